@@ -1,0 +1,134 @@
+/* C ABI of the B200 batched VI-ESKF engine (libeskf_b200.so).
+ *
+ * The reference (salehahr/dvi-ekf) is pure Python and has no FFI; the seam this
+ * library sits behind is the Python class dvi_ekf/filter/Filter.py:28 (`Filter`)
+ * and its driver dvi_ekf/filter/Simulator.py:24.  Each entry point below names the
+ * reference method it replaces.  Plain pointers and sizes only; every function
+ * returns 0 on success or a negative ESKF_E* code and never throws.  A handle is
+ * bound to one device + stream, is not thread-safe, and all calls are ordered on
+ * that stream (asynchronous w.r.t. the host unless a host buffer has to be read
+ * back, in which case the call synchronises the stream before returning).
+ *
+ * Layouts (row-major FP64):
+ *   x      [N,26]  p(3) v(3) q_xyzw(4) dofs(6) notch,notch_d,notch_dd(3) p_cam(3) q_cam_xyzw(4)
+ *                  (dvi_ekf/filter/state.py:11-29)
+ *   P      [N,24,24] error covariance, error-state order dp dv dth ddofs(6) dnotch(3) dpc dthc
+ *                  (state.py:105-115)
+ *   u_old  [N,6]   previous IMU sample om(3), acc(3)      (Filter.py:78-79,225-226)
+ *   R_old  [N,9]   rot(q) at the end of the last propagate (Filter.py:80,227; NOT refreshed by update)
+ *   Qdiag  [N|1,13], Rdiag [N|1,7], sigma_om [N|1,3]      (Filter.py:68-75,330-331)
+ */
+#ifndef ESKF_B200_H
+#define ESKF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct eskf_handle eskf_t;
+
+enum { ESKF_MEM_HOST = 0, ESKF_MEM_DEVICE = 1 };
+
+enum {
+  ESKF_OK = 0,
+  ESKF_EINVAL = -1,  /* bad argument */
+  ESKF_ECUDA = -2,   /* CUDA runtime error (see eskf_last_error) */
+  ESKF_ENOMEM = -3
+};
+
+/* model flags */
+enum { ESKF_FLAG_ZERO_FROZEN = 1 /* HEAD behaviour, Filter.py:243-245 */ };
+
+/* per-filter status bits (eskf_get_state) */
+enum {
+  ESKF_STATUS_UPDATE_SKIPPED = 1, /* singular / non-finite S: the LinAlgError branch, Filter.py:356-361 */
+  ESKF_STATUS_ASIN_DOMAIN = 2     /* |v| > 1 in Quaternion.angle (math.asin would raise) */
+};
+
+typedef struct {
+  double scope_length;   /* config.yaml model.length              (Probe.py:162) */
+  double cam_angle_rad;  /* config.yaml model.angle, in radians    (config.py:130-132) */
+  int32_t frozen_mask;   /* bit i set: DOF i frozen                (Filter.py:56) */
+  int32_t flags;         /* ESKF_FLAG_* */
+} eskf_model_t;
+
+/* Trajectory streams for eskf_run == Filter.run (Filter.py:144-185).
+ * All arrays live in `mem` space.  n_traj trajectories are stacked; filter i uses
+ * trajectory (filter_id0 + i) / filters_per_traj  (n_traj = 1: every filter shares one). */
+typedef struct {
+  int64_t n_steps;          /* T: IMU samples per trajectory */
+  int64_t n_epochs;         /* E: camera frames after the initial one */
+  int32_t n_traj;
+  int32_t mem;              /* ESKF_MEM_* */
+  int64_t filters_per_traj;
+  const double* dt;         /* [n_traj,T]   per-step dt (Filter.py:214; quirk Q14: never assumed uniform) */
+  const double* om_acc;     /* [n_traj,T,6] IMU samples (Imu.eval_expr_single, Imu.py:141-196) */
+  const int32_t* n_prop;    /* [n_traj,E]   IMU samples in each epoch (Camera.py:320-347) */
+  const double* cam;        /* [n_traj,E,7] camera position + RAW quaternion xyzw (VisualTrajectory.py:120-134) */
+  const double* notch;      /* [n_traj,E]   measured notch angle (Camera.get_notch_vec_at) */
+  /* references for the error statistics (nullable: statistics then only hold the DOF error) */
+  const double* cam_ref;    /* [n_traj,E,6] camera x y z rx ry rz(deg)      (Filter.py:401-406) */
+  const double* imu_ref;    /* [n_traj,E,6] IMU ref vx vy vz rx ry rz(deg)  (Filter.py:408-413) */
+  double gt_dofs[6];        /* config.gt_imu_dofs (Filter.py:452-455) */
+  /* Monte-Carlo extension (the reference is noise free): zero-mean Gaussian noise drawn
+   * in-kernel from Philox4x32-10(key = seed, counter = (step, kind, filter id)) */
+  uint64_t seed;
+  int64_t filter_id0;       /* global id of this handle's first filter (multi-GPU sharding) */
+  double imu_noise_std[6];  /* added to om(3), acc(3) of every IMU sample */
+  double cam_noise_std[7];  /* added to camera position(3), as small rotation(3), notch(1) */
+  int32_t noise_free_filter0; /* global filter 0 stays noise free (= the oracle run) */
+  int32_t reserved;
+} eskf_streams_t;
+
+#define ESKF_NSTAT 16
+/* per-filter statistics row written by eskf_run: [0:6] (dofs - gt)^2, [6] dof metric (Filter.py:452-455),
+ * [7] update_mse of the last epoch (Filter.py:397-418), [8] sum of update_mse over epochs,
+ * [9] number of applied updates, [10] status, [11:16] reserved */
+
+/* Simulator.__init__ / Filter.__init__ (Simulator.py:30-68, Filter.py:34-93) */
+int eskf_create(const eskf_model_t* model, int64_t n_filters, int device, void* cuda_stream, eskf_t** out);
+int eskf_destroy(eskf_t* h);
+
+/* Filter.__init__ / Filter.reset (Filter.py:44-45,78-80,95-108).  nx, nP, nu, nR are the leading
+ * dimensions of the arrays passed: N, or 1 to broadcast one row to every filter.
+ * R_old may be NULL: it is then set to rot(q) (Filter.py:80). */
+int eskf_set_state(eskf_t* h, const double* x, int64_t nx, const double* P, int64_t nP, const double* u_old,
+                   int64_t nu, const double* R_old, int64_t nR, int mem);
+
+/* Filter.__init__ noise setup / update_noise_matrices (Filter.py:68-75,110-117) */
+int eskf_set_noise(eskf_t* h, const double* Qdiag, int64_t nq, const double* Rdiag, int64_t nr,
+                   const double* sigma_om, int64_t ns, int mem);
+
+/* T calls of Filter.propagate(t, om, acc) (Filter.py:219-230) on every filter.
+ * om_acc is [T,6] (per_filter = 0) or [N,T,6] (per_filter = 1); dt is [T]. */
+int eskf_propagate(eskf_t* h, const double* dt, const double* om_acc, int64_t T, int per_filter, int mem);
+
+/* Filter.update(t, camera, ang_notch) -> K (Filter.py:351-395).  cam is [1,7] / [N,7]
+ * (position + raw quaternion xyzw), notch [1] / [N].  K_out is NULL or [N,24,7]. */
+int eskf_update(eskf_t* h, const double* cam, const double* notch, int per_filter, double* K_out, int mem);
+
+/* Filter.run (Filter.py:144-185): the whole trajectory in ONE persistent kernel, covariance resident
+ * on-chip.  stats_out is NULL or [N,ESKF_NSTAT]; stats_sum is NULL or [ESKF_NSTAT] (sum over this
+ * handle's filters, the vector a multi-GPU launcher all-reduces). */
+int eskf_run(eskf_t* h, const eskf_streams_t* streams, double* stats_out, double* stats_sum, int mem);
+
+/* Filter._states / _P / buffers read-back.  Any pointer may be NULL. */
+int eskf_get_state(eskf_t* h, double* x, double* P, double* u_old, double* R_old, int32_t* status, int mem);
+
+/* blocks until everything queued on the handle's stream has finished */
+int eskf_sync(eskf_t* h);
+
+/* number of kernels this library has launched on the handle so far */
+int64_t eskf_launch_count(const eskf_t* h);
+/* filters per CTA used for the kernels (tunable; 0 = automatic) */
+int eskf_set_tuning(eskf_t* h, int filters_per_cta);
+
+const char* eskf_last_error(void);
+const char* eskf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESKF_B200_H */

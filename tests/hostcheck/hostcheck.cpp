@@ -1,0 +1,75 @@
+// CPU harness around dvi_ekf_b200/csrc/eskf_math.cuh (TEST INFRASTRUCTURE).
+// Compiles the exact host/device math header with g++ and replays, sequentially,
+// what one CTA does for one filter: the scalar role followed by the eight
+// covariance lanes (column pass, then row pass).  Lets the not-gpu test suite
+// check the device arithmetic against the oracle without a GPU.
+#include "../../dvi_ekf_b200/csrc/eskf_math.cuh"
+#include <string.h>
+
+using namespace eskf;
+
+static void load_nominal(Nominal& s, const double* x, const double* u, const double* Ro) {
+  memcpy(s.p, x + 0, 24); memcpy(s.v, x + 3, 24); memcpy(s.q, x + 6, 32);
+  memcpy(s.dofs, x + 10, 48); memcpy(s.notch, x + 16, 24); memcpy(s.pc, x + 19, 24); memcpy(s.qc, x + 22, 32);
+  memcpy(s.om_old, u, 24); memcpy(s.acc_old, u + 3, 24); memcpy(s.R_old, Ro, 72);
+}
+static void store_nominal(const Nominal& s, double* x, double* u, double* Ro) {
+  memcpy(x + 0, s.p, 24); memcpy(x + 3, s.v, 24); memcpy(x + 6, s.q, 32);
+  memcpy(x + 10, s.dofs, 48); memcpy(x + 16, s.notch, 24); memcpy(x + 19, s.pc, 24); memcpy(x + 22, s.qc, 32);
+  memcpy(u, s.om_old, 24); memcpy(u + 3, s.acc_old, 24); memcpy(Ro, s.R_old, 72);
+}
+
+extern "C" {
+
+// model = {L, angle, frozen_mask, flags}
+void hc_propagate(const double* model, double* x, double* P, double* u, double* Ro, double dt, const double* om_acc,
+                  const double* qd, const double* sig_om, double* fx_out) {
+  Model m{model[0], sin(model[1]), cos(model[1]), (int)model[2], (int)model[3]};
+  Nominal s; load_nominal(s, x, u, Ro);
+  ProbeKin pk; ProbeTrig t;
+  probe_eval(m, s.dofs, s.notch, pk, t);
+  double R_WB[9]; quat_to_rot(s.q, R_WB);
+  double fx[FX_STRIDE];
+  const bool imu_q = (qd[3] != 0.0) || (qd[4] != 0.0) || (qd[5] != 0.0);
+  propagate_scalar(m, s, pk, R_WB, dt, om_acc, om_acc + 3, sig_om, imu_q, fx);
+  constexpr int RS = 25;
+  double Ps[24 * RS];
+  for (int i = 0; i < 24; ++i) for (int j = 0; j < 24; ++j) Ps[i * RS + j] = P[i * 24 + j];
+  for (int g = 0; g < 8; ++g) fx_apply3<RS, 1>(Ps + 3 * g, fx);          // T = Fx P   (columns)
+  for (int g = 0; g < 8; ++g) {                                            // P' = T Fx^T (rows) + Fi Q Fi^T
+    fx_apply3<1, RS>(Ps + 3 * g * RS, fx);
+    add_process_noise3<1, RS>(Ps + 3 * g * RS, 3 * g, fx, qd, imu_q);
+  }
+  for (int i = 0; i < 24; ++i) for (int j = 0; j < 24; ++j) P[i * 24 + j] = Ps[i * RS + j];
+  store_nominal(s, x, u, Ro);
+  if (fx_out) memcpy(fx_out, fx, sizeof(double) * FX_SIZE);
+}
+
+// returns 1 if the update was applied, 0 if skipped (singular S)
+int hc_update(const double* model, double* x, double* P, const double* u, const double* Ro, const double* cam /*pos3 quat4*/,
+              double notch, const double* rd, double* K_out) {
+  Model m{model[0], sin(model[1]), cos(model[1]), (int)model[2], (int)model[3]};
+  Nominal s; double uu[6], RR[9]; memcpy(uu, u, 48); memcpy(RR, Ro, 72);
+  load_nominal(s, x, uu, RR);
+  constexpr int RS = 25;
+  double Ps[24 * RS];
+  for (int i = 0; i < 24; ++i) for (int j = 0; j < 24; ++j) Ps[i * RS + j] = P[i * 24 + j];
+  double up[UP_SIZE];
+  double S[49];
+  for (int a = 0; a < 7; ++a) for (int b = 0; b < 7; ++b) S[7 * a + b] = Ps[ESKF_HSET(a) * RS + ESKF_HSET(b)] + (a == b ? rd[a] : 0.0);
+  bool ok = inv7(S, up + UP_SINV);
+  ok = update_residual(s, cam, cam + 3, notch, up + UP_RES) && ok;
+  if (!ok) return 0;
+  for (int g = 0; g < 8; ++g) gain_rows3<RS>(Ps, 3 * g, up);
+  inject_error(m, s, up + UP_DELTA);
+  for (int g = 0; g < 8; ++g) joseph_apply3<RS, 1>(Ps + 3 * g, up);
+  for (int g = 0; g < 8; ++g) joseph_rows_finish3<RS>(Ps + 3 * g * RS, 3 * g, up, rd);
+  for (int i = 0; i < 24; ++i) for (int j = 0; j < 24; ++j) P[i * 24 + j] = Ps[i * RS + j];
+  store_nominal(s, x, uu, RR);
+  if (K_out)
+    for (int r = 0; r < 24; ++r) for (int mm = 0; mm < 7; ++mm)
+      K_out[7 * r + mm] = (ESKF_HSET(mm) == r) ? up[UP_KD + mm] : up[UP_KZ + 7 * r + mm];
+  return 1;
+}
+
+}  // extern "C"
