@@ -174,6 +174,8 @@ __global__ void __launch_bounds__(32 + 8 * F, 1) eskf_kernel(const __grid_consta
   const int ct = tid - 32;
   const int cf = ct >> 3;  // filter of this covariance lane (padded filters run on an identity P, never stored)
   const int cg = ct & 7;   // state group owned
+  // the eight lanes of a filter group always take the same branches: group-level barriers use this mask
+  const unsigned gmask = 0xffu << (tid & 24);
 
   // trajectory of this CTA (all filters of a CTA share it: host guarantees filters_per_traj % F == 0)
   const int64_t gid0 = a.filter_id0 + f0;
@@ -273,10 +275,10 @@ __global__ void __launch_bounds__(32 + 8 * F, 1) eskf_kernel(const __grid_consta
       } else if (it >= 1) {
         const double* fx = scr_c + ((it - 1) & 1) * FX_STRIDE;
         fx_apply3<P_RS, 1>(Pf + 3 * cg, fx);  // T = Fx P      (columns 3g..3g+2)
-        __syncwarp();
+        __syncwarp(gmask);
         fx_apply3<1, P_RS>(Pf + 3 * cg * P_RS, fx);  // P' = T Fx^T   (rows 3g..3g+2)
         add_process_noise3<1, P_RS>(Pf + 3 * cg * P_RS, 3 * cg, fx, par_c + PAR_QD, imu_q);
-        __syncwarp();
+        __syncwarp(gmask);
       }
       __syncthreads();
     }
@@ -375,9 +377,9 @@ __global__ void __launch_bounds__(32 + 8 * F, 1) eskf_kernel(const __grid_consta
         }
       }
       joseph_apply3<P_RS, 1>(Pf + 3 * cg, scr_c);  // (I-KH) P
-      __syncwarp();
+      __syncwarp(gmask);
       joseph_rows_finish3<P_RS>(Pf + 3 * cg * P_RS, 3 * cg, scr_c, par_c + PAR_RD);  // (.)(I-KH)^T + K R K^T, reset
-      __syncwarp();
+      __syncwarp(gmask);
     }
     __syncthreads();  // the update record shares storage with the fx buffers
   }
