@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""Benchmark of the batched VI-ESKF hot path (BASELINE.json metric: ESKF filter-steps/sec).
+
+One "step" of this benchmark = one pass of the hot path over one batch: every filter of the batch runs
+the whole default simulated trajectory (mandala0_mono, 140 camera frames, 10 IMU samples per frame:
+1390 x Filter.propagate + 139 x Filter.update) inside ONE persistent kernel launch.  One *filter-step*
+(the metric's unit) = one Filter.propagate on one filter.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--filters F] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU); every rank runs its own shard of the Monte-Carlo batch
+(weak scaling: --filters is per GPU; Philox noise is keyed by the GLOBAL filter id) and the only
+collective is the all-reduce of the 16-entry error-statistics vector, inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "eskf_filter_steps_per_sec"
+UNIT = "filter-steps/s"
+N_FRAMES, IFV = 140, 10
+# algorithmic FP64 flops per filter-step, SURVEY.md section 8(d) / BASELINE.md section 5 (ifv = 10)
+F_MIN_PER_STEP = 9031 + 29587 / IFV  # structure-aware lower bound  (11,990)
+F_DENSE_PER_STEP = 78960 + 160767 / IFV  # reference-as-executed dense matmuls (95,037)
+SEED = 1234
+
+
+class Workload:
+    """Config 2 of BASELINE.md: the default simulated trajectory (full variant: 140 frames, 10 IMU samples per
+    frame), HEAD behaviour, built by the PRODUCT's host pre-pass (dvi_ekf_b200.camera) from config.yaml."""
+
+    def __init__(self):
+        from dvi_ekf_b200.camera import Camera, build_streams, load_trajectory
+        from dvi_ekf_b200.config import Config
+
+        cfg = Config(os.path.join(ROOT, "config.yaml"))
+        cfg.update_dofs()
+        self.cfg = cfg
+        t, xyz, q = load_trajectory("mandala0_mono", max_vals=N_FRAMES)
+        cam = Camera(t, xyz, q, scale=cfg.camera.scale)
+        self.s = build_streams(cam, IFV, cfg.model.length, cfg.model.angle)
+        self.P0 = cfg.cov0_matrix
+        rw = cfg.filter.noise_dofs.vec / IFV  # config.py:258 with interframe_vals = 10
+        self.Qd = np.hstack((np.zeros(6), np.square(rw)))  # Q[0:6] = 0: Filter.py:40,68-72
+        self.Rd = np.square(cfg.meas_noise_std)
+        self.sig_om = np.array(cfg.imu.stdev_omega)
+        self.imu_std = np.hstack((cfg.imu.stdev_omega, cfg.imu.stdev_accel))  # config.py:105-120
+        self.cam_std = np.array(cfg.meas_noise_std)  # config.yaml:20-23
+        self.model = dict(scope_length=cfg.model.length, cam_angle_rad=cfg.model.angle, frozen_dofs=cfg.frozen_dofs,
+                          zero_frozen_dofs=True)
+
+
+def mc_initial_states(x0_row, n, first_id):
+    """DOF initial-condition perturbation N(0, 3 deg) / N(0, 3 cm) (commented intent at
+    dvi_ekf/tools/utils.py:28-33); global filter 0 keeps the ground truth."""
+    x0 = np.repeat(x0_row[None], n, 0)
+    for i in range(n):
+        gid = first_id + i
+        if gid == 0:
+            continue
+        rng = np.random.default_rng([SEED, gid])
+        x0[i, 10:13] += rng.normal(0.0, np.deg2rad(3.0), 3)
+        x0[i, 13:16] += rng.normal(0.0, 3.0, 3)
+    return x0
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the batch-vectorised numpy oracle (a port: the reference itself needs casadi /
+# roboticstoolbox, which are not installable here -- DESIGN.md)
+
+
+def _cpu_worker(args):
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    n, n_epochs, seed = args
+    from oracle.batch_oracle import BatchOracle
+    from tests.helpers import mandala_scenario
+
+    sc = mandala_scenario(np.load(os.path.join(ROOT, "tests", "golden", "reference_golden.npz")), n_frames=N_FRAMES, ifv=IFV)
+    rng = np.random.default_rng(seed)
+    x0 = np.repeat(sc.x0[None], n, 0)
+    x0[:, 10:13] += rng.normal(0.0, np.deg2rad(3.0), (n, 3))
+    bo = BatchOracle(sc.cfg, x0, sc.P0, sc.u0)
+    t0 = time.perf_counter()
+    steps = bo.run(sc.dt, sc.om_acc, sc.n_prop[:n_epochs], sc.cam_meas, sc.notch_meas)
+    return n * steps, time.perf_counter() - t0
+
+
+def cpu_sample(procs, filters_per_proc, n_epochs):
+    """Runs the batch oracle on `procs` host processes; returns (filter-steps, seconds)."""
+    import multiprocessing as mp
+
+    jobs = [(filters_per_proc, n_epochs, 100 + i) for i in range(procs)]
+    t0 = time.perf_counter()
+    if procs == 1:
+        res = [_cpu_worker(jobs[0])]
+    else:
+        with mp.get_context("spawn").Pool(procs) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    work = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)  # slowest worker, excludes interpreter start-up
+    return work, busy, wall
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    fpp, n_epochs = 256, 8  # bounded sample: cores x 256 filters x 8 epochs (80 propagates + 8 updates)
+    for _ in range(a.warmup):
+        cpu_sample(cores, 32, 1)
+    times, work = [], 0
+    for _ in range(a.steps):
+        w, busy, _ = cpu_sample(cores, fpp, n_epochs)
+        times.append(busy)
+        work = w
+    ms = 1e3 * float(np.mean(times))
+    val = work / (ms * 1e-3)
+    sample = f"{cores} procs x {fpp} filters x {n_epochs} epochs ({n_epochs * IFV} propagates + {n_epochs} updates) per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config2: Monte-Carlo filters on the default simulated trajectory (mandala0_mono, "
+                               "140 frames x 10 IMU samples), bounded sample", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "numpy batch-vectorised port of the reference algorithm (oracle/batch_oracle.py); the reference itself "
+                "cannot be installed here (casadi, roboticstoolbox, spatialmath absent; pydantic v2) and would be slower",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            pass
+    return None
+
+
+def run_ours(a):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = Workload()
+    sc = wl.s
+    T, E = len(sc.dt), len(sc.n_prop)
+
+    # CPU baseline first (rank 0, single-GPU runs only; before CUDA is initialised in this process)
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        fpp, n_ep = 256, 8
+        work, busy, wall = cpu_sample(cores, fpp, n_ep)
+        cpu = {"value": work / busy, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{cores} procs x {fpp} filters x {n_ep} epochs of the same trajectory "
+                         f"({work} filter-steps in {busy:.1f} s; numpy batch oracle, oracle/batch_oracle.py)"}
+
+    import torch
+
+    from dvi_ekf_b200 import BatchFilter
+    from dvi_ekf_b200.engine import fp64_peak_tflops
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    n = a.filters
+    first_id = rank * n
+    imu_std, cam_std = wl.imu_std, wl.cam_std
+
+    def dt64(x, dtype=torch.float64):
+        return torch.tensor(np.ascontiguousarray(x), dtype=dtype, device=dev)
+
+    # references for the update-MSE statistic (Filter.calculate_update_mse, Filter.py:397-418)
+    cam_ref, imu_ref = sc.cam_ref, sc.imu_ref
+    x0_host = mc_initial_states(sc.x0, n, first_id)
+    d = dict(dt=dt64(sc.dt), oa=dt64(sc.om_acc), npr=dt64(sc.n_prop, torch.int32), cam=dt64(sc.cam),
+             notch=dt64(sc.notch), cam_ref=dt64(cam_ref), imu_ref=dt64(imu_ref), x0=dt64(x0_host),
+             P0=dt64(wl.P0[None]), u0=dt64(sc.u0[None]))
+    bf = BatchFilter(n, device=local, **wl.model)
+    bf.set_tuning(a.fpc)
+    bf.set_noise(wl.Qd[None], wl.Rd[None], wl.sig_om[None])
+    run_kw = dict(gt_dofs=(0, 0, 0, 0, 0, 20.0), seed=SEED, filter_id0=first_id, imu_noise_std=imu_std,
+                  cam_noise_std=cam_std, noise_free_filter0=True)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
+
+    def one_pass():
+        st, sm = bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], cam_ref=d["cam_ref"], imu_ref=d["imu_ref"],
+                        stats_on_device=True, **run_kw)
+        if dist is not None:
+            dist.all_reduce(sm)
+        return st, sm
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reset():
+        bf.set_state(d["x0"], d["P0"], d["u0"], None)
+        flush.zero_()  # evict L2 between timed iterations
+
+    for _ in range(max(a.warmup, 3)):
+        reset()
+        one_pass()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = bf.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    launches_timed = 0
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(a.steps):
+        reset()
+        lb = bf.launch_count
+        ev[i][0].record()
+        st, sm = one_pass()
+        ev[i][1].record()
+        launches_timed += bf.launch_count - lb
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ms_steps = [e0.elapsed_time(e1) for e0, e1 in ev]
+    ms = float(np.mean(ms_steps))
+    # keep the hardware busy for the clock sampler a little longer on very short runs
+    clocks = sampler.stop() if rank == 0 else None
+    stats_sum = sm.cpu().numpy()
+
+    # ---- end-to-end through the C ABI with HOST buffers (pinned), copies inside the timed region ----
+    def pinned(x, dtype=np.float64):
+        t = torch.from_numpy(np.ascontiguousarray(x, dtype=dtype)).pin_memory()
+        return t.numpy(), t
+
+    keep = []
+    hp = {}
+    for k, v in dict(dt=sc.dt, oa=sc.om_acc, cam=sc.cam, notch=sc.notch, cam_ref=cam_ref, imu_ref=imu_ref,
+                     x0=x0_host, P0=wl.P0[None], u0=sc.u0[None]).items():
+        hp[k], t = pinned(v)
+        keep.append(t)
+    hp["npr"], t = pinned(sc.n_prop, np.int32)
+    keep.append(t)
+    h2d = sum(hp[k].nbytes for k in ("dt", "oa", "npr", "cam", "notch", "cam_ref", "imu_ref", "x0", "P0", "u0"))
+    d2h = n * 16 * 8 + 16 * 8
+
+    def e2e_pass():
+        bf.set_state(hp["x0"], hp["P0"], hp["u0"], None)
+        st_h, sm_h = bf.run(hp["dt"], hp["oa"], hp["npr"], hp["cam"], hp["notch"], cam_ref=hp["cam_ref"],
+                            imu_ref=hp["imu_ref"], **run_kw)
+        if dist is not None:
+            t = torch.from_numpy(sm_h).to(dev)
+            dist.all_reduce(t)
+            sm_h = t.cpu().numpy()
+        return st_h, sm_h
+
+    for _ in range(2):
+        e2e_pass()
+    barrier()
+    e2e_ms = []
+    for _ in range(a.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st_h, sm_h = e2e_pass()  # returns after the D2H read of the statistics
+        e2e_ms.append(1e3 * (time.perf_counter() - t0))
+    barrier()
+    e2e_t = float(np.mean(e2e_ms))
+
+    # max over ranks
+    if dist is not None:
+        tt = torch.tensor([ms, e2e_t], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_t = float(tt[0]), float(tt[1])
+    total_steps = float(n) * T * world
+    value = total_steps / (ms * 1e-3)
+    e2e_val = total_steps / (e2e_t * 1e-3)
+
+    if rank == 0:
+        peak_tf = fp64_peak_tflops(local)
+        peaks, which = measured_peaks()
+        per_launch_flops = float(n) * T * F_MIN_PER_STEP
+        ach = per_launch_flops / (ms * 1e-3) * 1e-12
+        alg_bytes = float(n) * (2 * (576 + 26 + 6 + 9) * 8 + 16 * 8) + (T * 7 + E * 21) * 8  # state in/out + streams
+        tr = ncu_traffic()
+        roofline = {
+            "bound": "fp64",
+            "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+            "peak_source": "eskf_fp64_peak(): pure-DFMA kernel timed in this run (MEASURED_PEAKS.json has no FP64 figure; "
+                           "nominal 37 TFLOP/s at 1965 MHz)",
+            "flops_per_filter_step": F_MIN_PER_STEP,
+            "dense_equiv": {"achieved": float(n) * T * F_DENSE_PER_STEP / (ms * 1e-3) * 1e-12,
+                            "flops_per_filter_step": F_DENSE_PER_STEP},
+            "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (ms * 1e-3) * 1e-9,
+                    "peak_gbs": peaks.get("hbm_gbs"), "peak_source": which + " (MEASURED_PEAKS.json)"},
+            "traffic": (tr or {}).get("dram_bytes_per_launch"),
+            "kernel": "eskf::eskf_kernel<F> (one launch per pass)",
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": f"config2: {n} Monte-Carlo filters per GPU (Philox noise seeds, DOF IC perturbation) on the default "
+                            f"simulated trajectory mandala0_mono, {N_FRAMES} frames x {IFV} IMU samples "
+                            f"({T} propagates + {E} updates per filter per pass)",
+                "filters_per_gpu": n, "filter_steps_per_pass": int(n) * T * world, "l2": "flushed between timed iterations "
+                "(256 MiB memset)", "filters_per_cta": a.fpc or "auto", "parallelism": f"filters sharded over {world} GPU(s)",
+            },
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_t},
+            "gpu_launches": int(launches_timed),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "wall_s_timed_loop": t_wall,
+            "stats": {"dof_rmse": [float(np.sqrt(v / stats_sum[11])) for v in stats_sum[:6]],
+                      "mean_update_mse_last": float(stats_sum[7] / stats_sum[11]), "filters": float(stats_sum[11]),
+                      "updates_applied": float(stats_sum[9])},
+        }
+        print(json.dumps(line), flush=True)
+    bf.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--filters", type=int, default=4096, help="filters per GPU (BASELINE config 2: 4096)")
+    ap.add_argument("--fpc", type=int, default=0, help="filters per CTA (0 = automatic)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        return run_reference_arm(a)
+    return run_ours(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libeskf_b200.so")
+LIB_PATH = os.environ.get("ESKF_B200_LIB") or os.path.join(HERE, "libeskf_b200.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
 FLAG_ZERO_FROZEN = 1
@@ -19,7 +19,7 @@ NSTAT = 16
 EXPORTS = (
     "eskf_create", "eskf_destroy", "eskf_set_state", "eskf_set_noise", "eskf_propagate", "eskf_update",
     "eskf_run", "eskf_get_state", "eskf_sync", "eskf_launch_count", "eskf_set_tuning", "eskf_last_error",
-    "eskf_version",
+    "eskf_version", "eskf_fp64_peak",
 )
 
 
@@ -87,6 +87,7 @@ def load():
     lib.eskf_launch_count.argtypes = [vp]
     lib.eskf_launch_count.restype = i64
     lib.eskf_set_tuning.argtypes = [vp, i32]
+    lib.eskf_fp64_peak.argtypes = [i32, vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.eskf_last_error.restype = C.c_char_p
     lib.eskf_version.restype = C.c_char_p
     for name in EXPORTS:

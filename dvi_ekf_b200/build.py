@@ -48,7 +48,14 @@ def _run(cmd, log):
     return p.stdout
 
 
-def build_cuda(force: bool = False, verbose: bool = False) -> str:
+def build_cuda(force: bool = False, verbose: bool = False, defines=(), suffix: str = "") -> str:
+    """``defines`` / ``suffix`` build an experiment variant (e.g. -DESKF_EXP_NO_COV) next to the product
+    library as libeskf_b200<suffix>.so; select it at run time with ESKF_B200_LIB=<path>."""
+    global OBJ, LIB
+    if suffix:
+        OBJ = os.path.join(HERE, "build" + suffix)
+        LIB = os.path.join(HERE, f"libeskf_b200{suffix}.so")
+    extra = [f"-D{d}" for d in defines]
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, h) for h in ("eskf_math.cuh", "eskf_rng.cuh", "eskf_kernel.cuh")]
     headers.append(os.path.join(ROOT, "include", "eskf.h"))
@@ -56,10 +63,10 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     for f in SHAPES:
         obj = os.path.join(OBJ, f"eskf_launch_f{f}.o")
         src = os.path.join(CSRC, "eskf_launch.cu")
-        jobs.append((obj, [src] + headers, [_nvcc(), *NVCC_FLAGS, f"-DESKF_F={f}", "-c", src, "-o", obj]))
+        jobs.append((obj, [src] + headers, [_nvcc(), *NVCC_FLAGS, *extra, f"-DESKF_F={f}", "-c", src, "-o", obj]))
     api_obj = os.path.join(OBJ, "eskf_api.o")
     api_src = os.path.join(CSRC, "eskf_api.cu")
-    jobs.append((api_obj, [api_src] + headers, [_nvcc(), *NVCC_FLAGS, "-c", api_src, "-o", api_obj]))
+    jobs.append((api_obj, [api_src] + headers, [_nvcc(), *NVCC_FLAGS, *extra, "-c", api_src, "-o", api_obj]))
     todo = [(o, c) for (o, srcs, c) in jobs if force or not _newer(o, srcs)]
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(todo)))) as ex:
         outs = list(ex.map(lambda oc: _run(oc[1], oc[0] + ".log"), todo))
@@ -95,6 +102,11 @@ def ptxas_summary() -> str:
 
 
 if __name__ == "__main__":
+    for a in sys.argv[1:]:
+        if a.startswith("--exp="):  # e.g. --exp=ESKF_EXP_NO_COV
+            d = a.split("=", 1)[1]
+            print(build_cuda(defines=(d,), suffix="_" + d.lower()))
+            sys.exit(0)
     print(build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_hostcheck())
     print(ptxas_summary())

@@ -47,6 +47,23 @@ __global__ void fill_par_kernel(double* par, const double* q, int64_t nq, const 
   p[PAR_SIZE] = 0.0;
 }
 
+// FP64 FMA throughput probe: ILP independent DFMA chains per thread, nothing else in the loop.
+// Used by bench.py to measure the roofline denominator (MEASURED_PEAKS.json has no FP64 figure).
+template <int ILP>
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double acc[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) acc[i] = (double)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) s += acc[i];
+  if (s == 123.456) out[0] = s;  // keeps the chain alive without a store in the common case
+}
+
 thread_local std::string g_err;
 
 }  // namespace
@@ -106,21 +123,32 @@ static int stage_in(eskf_t* h, int slot, const void* src, size_t bytes, int mem,
 static const int kShapes[] = {28, 24, 20, 16, 12, 8, 4};
 
 // Filters per CTA.  Must divide filters_per_traj when several trajectories are stacked (a CTA follows
-// ONE trajectory's epoch structure).  Automatic choice: the largest shape that still leaves every SM
-// with at least two CTAs' worth of filters; smaller batches use the smallest shape so that the
-// latency-bound scalar role is spread over as many warps as possible.
+// ONE trajectory's epoch structure).  The kernel is latency bound on the per-step critical path, so a
+// wave of CTAs takes about the same time whatever its shape (measured, profiles/r01_*): the automatic
+// choice minimises the number of waves and then prefers the larger shape (more filters per SM).
 static int pick_fpc(const eskf_t* h, int64_t fpt, bool multi_traj) {
   auto fits = [&](int c) { return !multi_traj || (fpt % c) == 0; };
   if (h->fpc > 0) {
     for (int c : kShapes)
       if (c == h->fpc && fits(c)) return c;
   }
-  const int64_t per_sm = (h->N + h->sm_count - 1) / h->sm_count;
-  for (int c : kShapes)
-    if (fits(c) && per_sm >= 2 * (int64_t)c) return c;
-  for (int c : {4, 8, 12, 16, 20, 24, 28})
-    if (fits(c)) return c;
-  return 0;
+  int best = 0;
+  int64_t best_waves = 0;
+  for (int c : kShapes) {  // descending
+    if (!fits(c)) continue;
+    const int threads = 32 + 8 * c;
+    const int by_regs = 256 / threads;  // 255 registers per thread
+    const int by_smem = (int)((227 * 1024) / ((size_t)c * SM_PER_FILTER * sizeof(double)));
+    int per_sm = by_regs < by_smem ? by_regs : by_smem;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t ctas = (h->N + c - 1) / c;
+    const int64_t waves = (ctas + (int64_t)h->sm_count * per_sm - 1) / ((int64_t)h->sm_count * per_sm);
+    if (best == 0 || waves < best_waves) {
+      best = c;
+      best_waves = waves;
+    }
+  }
+  return best;
 }
 
 static int launch(eskf_t* h, const KArgs& a, int64_t fpt, bool multi_traj) {
@@ -433,6 +461,40 @@ int eskf_sync(eskf_t* h) {
   if (!h) return ESKF_EINVAL;
   CK(cudaSetDevice(h->device));
   CK(cudaStreamSynchronize(h->stream));
+  return ESKF_OK;
+}
+
+int eskf_fp64_peak(int device, void* cuda_stream, int repeats, double* tflops_out, double* ms_out) {
+  if (!tflops_out || repeats < 1) return ESKF_EINVAL;
+  CK(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int smc = 0;
+  CK(cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, device));
+  double* d = nullptr;
+  CK(cudaMalloc(&d, 64));
+  constexpr int ILP = 16;
+  const int blocks = smc * 8, threads = 256, iters = 1 << 14;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  dfma_peak_kernel<ILP><<<blocks, threads, 0, st>>>(d, iters, 1.0000001, 1e-9);  // warm-up
+  double best = 1e30;
+  for (int r = 0; r < repeats; ++r) {
+    CK(cudaEventRecord(e0, st));
+    dfma_peak_kernel<ILP><<<blocks, threads, 0, st>>>(d, iters, 1.0000001, 1e-9);
+    CK(cudaEventRecord(e1, st));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  CK(cudaGetLastError());
+  const double flops = 2.0 * ILP * (double)iters * blocks * threads;
+  *tflops_out = flops / (best * 1e-3) * 1e-12;
+  if (ms_out) *ms_out = best;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
   return ESKF_OK;
 }
 

@@ -269,16 +269,20 @@ __global__ void __launch_bounds__(32 + 8 * F, 1) eskf_kernel(const __grid_consta
             for (int i = 0; i < 9; ++i) Rq[i] = s.R_old[i];
           }
           after_update = false;
+#ifndef ESKF_EXP_NO_SCALAR  // (profiling experiment switch: time the covariance role alone)
           propagate_scalar(a.model, s, pk, Rq, dt, om, acc, sig_om, imu_q,
                            sScr + tid * SCR_STRIDE + (it & 1) * FX_STRIDE);
+#endif
         }
       } else if (it >= 1) {
+#ifndef ESKF_EXP_NO_COV  // (profiling experiment switch: time the scalar role alone)
         const double* fx = scr_c + ((it - 1) & 1) * FX_STRIDE;
         fx_apply3<P_RS, 1>(Pf + 3 * cg, fx);  // T = Fx P      (columns 3g..3g+2)
         __syncwarp(gmask);
         fx_apply3<1, P_RS>(Pf + 3 * cg * P_RS, fx);  // P' = T Fx^T   (rows 3g..3g+2)
         add_process_noise3<1, P_RS>(Pf + 3 * cg * P_RS, 3 * cg, fx, par_c + PAR_QD, imu_q);
         __syncwarp(gmask);
+#endif
       }
       __syncthreads();
     }

@@ -232,3 +232,11 @@ class BatchFilter:
 
     def set_tuning(self, filters_per_cta: int = 0):
         check(self._lib.eskf_set_tuning(self._h, int(filters_per_cta)), "eskf_set_tuning")
+
+
+def fp64_peak_tflops(device: int = 0, repeats: int = 5) -> float:
+    """Measured FP64 FMA throughput of the device (TFLOP/s): the roofline denominator of bench.py."""
+    lib = _lib.load()
+    out, ms = C.c_double(), C.c_double()
+    check(lib.eskf_fp64_peak(int(device), None, int(repeats), C.byref(out), C.byref(ms)), "eskf_fp64_peak")
+    return float(out.value)

@@ -125,6 +125,10 @@ int64_t eskf_launch_count(const eskf_t* h);
 /* filters per CTA used for the kernels (tunable; 0 = automatic) */
 int eskf_set_tuning(eskf_t* h, int filters_per_cta);
 
+/* Measurement aid (no reference counterpart): sustained FP64 FMA throughput of the device in
+ * TFLOP/s (best of `repeats` launches of a pure DFMA kernel) -- the roofline denominator. */
+int eskf_fp64_peak(int device, void* cuda_stream, int repeats, double* tflops_out, double* ms_out);
+
 const char* eskf_last_error(void);
 const char* eskf_version(void);
 
