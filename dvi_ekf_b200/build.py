@@ -18,7 +18,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libeskf_b200.so")
-SHAPES = (4, 8, 12, 16, 20, 24, 28)  # filters per CTA; keep in sync with eskf_api.cu
+SHAPES = (4, 8, 12, 16, 20, 24, 28)  # filters per CTA of eskf_kernel (v1); keep in sync with eskf_api.cu
+SHAPES2 = (4, 8, 16, 28)  # filters per CTA of eskf_kernel2 (v2)
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
@@ -57,12 +58,16 @@ def build_cuda(force: bool = False, verbose: bool = False, defines=(), suffix: s
         LIB = os.path.join(HERE, f"libeskf_b200{suffix}.so")
     extra = [f"-D{d}" for d in defines]
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, h) for h in ("eskf_math.cuh", "eskf_rng.cuh", "eskf_kernel.cuh")]
+    headers = [os.path.join(CSRC, h) for h in ("eskf_math.cuh", "eskf_rng.cuh", "eskf_kernel.cuh", "eskf_kernel2.cuh")]
     headers.append(os.path.join(ROOT, "include", "eskf.h"))
     jobs = []
     for f in SHAPES:
         obj = os.path.join(OBJ, f"eskf_launch_f{f}.o")
         src = os.path.join(CSRC, "eskf_launch.cu")
+        jobs.append((obj, [src] + headers, [_nvcc(), *NVCC_FLAGS, *extra, f"-DESKF_F={f}", "-c", src, "-o", obj]))
+    for f in SHAPES2:
+        obj = os.path.join(OBJ, f"eskf_launch2_f{f}.o")
+        src = os.path.join(CSRC, "eskf_launch2.cu")
         jobs.append((obj, [src] + headers, [_nvcc(), *NVCC_FLAGS, *extra, f"-DESKF_F={f}", "-c", src, "-o", obj]))
     api_obj = os.path.join(OBJ, "eskf_api.o")
     api_src = os.path.join(CSRC, "eskf_api.cu")
@@ -91,13 +96,14 @@ def build_hostcheck(force: bool = False) -> str:
 def ptxas_summary() -> str:
     """registers / spills / shared memory per kernel, from the saved nvcc logs."""
     lines = []
-    for f in SHAPES:
-        log = os.path.join(OBJ, f"eskf_launch_f{f}.o.log")
-        if os.path.exists(log):
-            txt = open(log).read().splitlines()
-            for i, l in enumerate(txt):
-                if "eskf_kernel" in l and "Compiling entry" in l:
-                    lines.append(f"F={f}: " + " | ".join(x.strip() for x in txt[i + 2 : i + 4]))
+    for tag, shapes in (("", SHAPES), ("2", SHAPES2)):
+        for f in shapes:
+            log = os.path.join(OBJ, f"eskf_launch{tag}_f{f}.o.log")
+            if os.path.exists(log):
+                txt = open(log).read().splitlines()
+                for i, l in enumerate(txt):
+                    if "eskf_kernel" in l and "Compiling entry" in l:
+                        lines.append(f"v{tag or 1} F={f}: " + " | ".join(x.strip() for x in txt[i + 2 : i + 4]))
     return "\n".join(lines)
 
 

@@ -8,7 +8,7 @@
 
 #include <string>
 
-#include "eskf_kernel.cuh"
+#include "eskf_kernel2.cuh"
 
 using namespace eskf;
 
@@ -16,6 +16,9 @@ namespace eskf {
 #define ESKF_DECL(F) template <> cudaError_t launch_eskf_kernel<F>(const KArgs& a, cudaStream_t stream);
 ESKF_DECL(4) ESKF_DECL(8) ESKF_DECL(12) ESKF_DECL(16) ESKF_DECL(20) ESKF_DECL(24) ESKF_DECL(28)
 #undef ESKF_DECL
+#define ESKF_DECL2(F) template <> cudaError_t launch_eskf_kernel2<F>(const KArgs& a, cudaStream_t stream);
+ESKF_DECL2(4) ESKF_DECL2(8) ESKF_DECL2(16) ESKF_DECL2(28)
+#undef ESKF_DECL2
 }  // namespace eskf
 
 namespace {
@@ -83,6 +86,7 @@ struct eskf_handle {
   double* stats_sum_dev = nullptr;
   int64_t launches = 0;
   int fpc = 0;  // filters per CTA (0 = automatic)
+  int variant = 0;  // 0 = default (v2), 1 = eskf_kernel (v1), 2 = eskf_kernel2 (v2)
   int sm_count = 148;
 };
 
@@ -120,29 +124,30 @@ static int stage_in(eskf_t* h, int slot, const void* src, size_t bytes, int mem,
   return ESKF_OK;
 }
 
-static const int kShapes[] = {28, 24, 20, 16, 12, 8, 4};
+static const int kShapes1[] = {28, 24, 20, 16, 12, 8, 4};  // eskf_kernel  (v1)
+static const int kShapes2[] = {28, 16, 8, 4};              // eskf_kernel2 (v2)
+
+static bool use_v2(const eskf_t* h) { return h->variant != 1; }
 
 // Filters per CTA.  Must divide filters_per_traj when several trajectories are stacked (a CTA follows
-// ONE trajectory's epoch structure).  The kernel is latency bound on the per-step critical path, so a
-// wave of CTAs takes about the same time whatever its shape (measured, profiles/r01_*): the automatic
-// choice minimises the number of waves and then prefers the larger shape (more filters per SM).
+// ONE trajectory's epoch structure).  Every shape runs one CTA per SM (registers / shared memory) and a
+// wave of CTAs takes about the same time whatever its shape (per-step latency bound, profiles/r01_*): the
+// automatic choice minimises the number of waves and then prefers the larger shape.
 static int pick_fpc(const eskf_t* h, int64_t fpt, bool multi_traj) {
   auto fits = [&](int c) { return !multi_traj || (fpt % c) == 0; };
+  const int* shapes = use_v2(h) ? kShapes2 : kShapes1;
+  const int ns = use_v2(h) ? 4 : 7;
   if (h->fpc > 0) {
-    for (int c : kShapes)
-      if (c == h->fpc && fits(c)) return c;
+    for (int i = 0; i < ns; ++i)
+      if (shapes[i] == h->fpc && fits(shapes[i])) return shapes[i];
   }
   int best = 0;
   int64_t best_waves = 0;
-  for (int c : kShapes) {  // descending
+  for (int i = 0; i < ns; ++i) {  // descending
+    const int c = shapes[i];
     if (!fits(c)) continue;
-    const int threads = 32 + 8 * c;
-    const int by_regs = 256 / threads;  // 255 registers per thread
-    const int by_smem = (int)((227 * 1024) / ((size_t)c * SM_PER_FILTER * sizeof(double)));
-    int per_sm = by_regs < by_smem ? by_regs : by_smem;
-    if (per_sm < 1) per_sm = 1;
     const int64_t ctas = (h->N + c - 1) / c;
-    const int64_t waves = (ctas + (int64_t)h->sm_count * per_sm - 1) / ((int64_t)h->sm_count * per_sm);
+    const int64_t waves = (ctas + h->sm_count - 1) / h->sm_count;
     if (best == 0 || waves < best_waves) {
       best = c;
       best_waves = waves;
@@ -153,17 +158,30 @@ static int pick_fpc(const eskf_t* h, int64_t fpt, bool multi_traj) {
 
 static int launch(eskf_t* h, const KArgs& a, int64_t fpt, bool multi_traj) {
   cudaError_t e;
-  switch (pick_fpc(h, fpt, multi_traj)) {
-    case 28: e = launch_eskf_kernel<28>(a, h->stream); break;
-    case 24: e = launch_eskf_kernel<24>(a, h->stream); break;
-    case 20: e = launch_eskf_kernel<20>(a, h->stream); break;
-    case 16: e = launch_eskf_kernel<16>(a, h->stream); break;
-    case 12: e = launch_eskf_kernel<12>(a, h->stream); break;
-    case 8: e = launch_eskf_kernel<8>(a, h->stream); break;
-    case 4: e = launch_eskf_kernel<4>(a, h->stream); break;
-    default:
-      g_err = "filters_per_traj must be a multiple of 4 when several trajectories are stacked";
-      return ESKF_EINVAL;
+  const int fpc = pick_fpc(h, fpt, multi_traj);
+  if (use_v2(h)) {
+    switch (fpc) {
+      case 28: e = launch_eskf_kernel2<28>(a, h->stream); break;
+      case 16: e = launch_eskf_kernel2<16>(a, h->stream); break;
+      case 8: e = launch_eskf_kernel2<8>(a, h->stream); break;
+      case 4: e = launch_eskf_kernel2<4>(a, h->stream); break;
+      default:
+        g_err = "filters_per_traj must be a multiple of 4 when several trajectories are stacked";
+        return ESKF_EINVAL;
+    }
+  } else {
+    switch (fpc) {
+      case 28: e = launch_eskf_kernel<28>(a, h->stream); break;
+      case 24: e = launch_eskf_kernel<24>(a, h->stream); break;
+      case 20: e = launch_eskf_kernel<20>(a, h->stream); break;
+      case 16: e = launch_eskf_kernel<16>(a, h->stream); break;
+      case 12: e = launch_eskf_kernel<12>(a, h->stream); break;
+      case 8: e = launch_eskf_kernel<8>(a, h->stream); break;
+      case 4: e = launch_eskf_kernel<4>(a, h->stream); break;
+      default:
+        g_err = "filters_per_traj must be a multiple of 4 when several trajectories are stacked";
+        return ESKF_EINVAL;
+    }
   }
   if (e != cudaSuccess) {
     g_err = std::string("eskf_kernel launch: ") + cudaGetErrorString(e);
@@ -190,7 +208,7 @@ static void base_args(const eskf_t* h, KArgs& a) {
 extern "C" {
 
 const char* eskf_last_error(void) { return g_err.c_str(); }
-const char* eskf_version(void) { return "eskf_b200 0.1 (sm_100a)"; }
+const char* eskf_version(void) { return "eskf_b200 0.2 (sm_100a)"; }
 
 int eskf_create(const eskf_model_t* model, int64_t n_filters, int device, void* cuda_stream, eskf_t** out) {
   if (!model || !out || n_filters <= 0) {
@@ -499,6 +517,12 @@ int eskf_fp64_peak(int device, void* cuda_stream, int repeats, double* tflops_ou
 }
 
 int64_t eskf_launch_count(const eskf_t* h) { return h ? h->launches : 0; }
+
+int eskf_set_variant(eskf_t* h, int variant) {
+  if (!h || variant < 0 || variant > 2) return ESKF_EINVAL;
+  h->variant = variant;
+  return ESKF_OK;
+}
 
 int eskf_set_tuning(eskf_t* h, int filters_per_cta) {
   if (!h || filters_per_cta < 0) return ESKF_EINVAL;

@@ -77,13 +77,14 @@ __device__ __forceinline__ void euler_xyz_deg(const double* q, double* e) {
 // column c of [S | I].  LU with partial pivoting + back substitution, the same operations in the same
 // order as eskf::inv7 (the host-checkable restatement of np.linalg.inv -> LAPACK gesv); multipliers
 // and U entries travel by width-8 shuffles.  Returns false for an exactly singular / non-finite S.
+template <int RS>
 __device__ __forceinline__ bool inv7_group(const double* Pf, const double* rd, int g, double* up) {
   const unsigned FULL = 0xffffffffu;
   const int c = (g < 7) ? g : 6;
   double a[7], b[7];
 #pragma unroll
   for (int i = 0; i < 7; ++i) {
-    a[i] = Pf[ESKF_HSET(i) * P_RS + ESKF_HSET(c)] + ((i == c) ? rd[c] : 0.0);
+    a[i] = Pf[ESKF_HSET(i) * RS + ESKF_HSET(c)] + ((i == c) ? rd[c] : 0.0);
     b[i] = (i == c) ? 1.0 : 0.0;
   }
   bool ok = true;
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(32 + 8 * F, 1) eskf_kernel(const __grid_consta
         up[UP_OK] = ok ? 1.0 : 0.0;
       }
     } else {
-      inv_ok = inv7_group(Pf, par_c + PAR_RD, cg, scr_c);
+      inv_ok = inv7_group<P_RS>(Pf, par_c + PAR_RD, cg, scr_c);
     }
     __syncthreads();
     // phase U1: gain rows, delta

@@ -864,4 +864,353 @@ ESKF_HD void joseph_rows_finish3(double* x, int r0, const double* up, const doub
   }
 }
 
+// =====================================================================================
+// v2 kernel building blocks: the same arithmetic as propagate_scalar / fx_apply3, cut along
+// the lines of the warp-specialised kernel (eskf_kernel2.cuh): IMU nominal state, camera
+// nominal state, Jacobian blocks, and the covariance transform on a register-resident tile.
+// tests/hostcheck replays them on the CPU against propagate_scalar / fx_apply3.
+// =====================================================================================
+
+// "fx2 record": Jacobian blocks laid out in the order the covariance role consumes them,
+// every row group starting on an even index so that it is fetched with 16-byte loads.
+constexpr int FX2_DT = 0;    // dt, pad
+constexpr int FX2_AB = 2;    // 3 x [A(i,0..2) B(i,0..2)]                     Fx[3:6,6:9], Fx[6:9,6:9]
+constexpr int FX2_R18 = 20;  // 3 x [C1(i,0..2) C2(i,0..5) pad]               Fx[18:21, 6:15]
+constexpr int FX2_R21 = 50;  // 3 x [D(i,0..3) E(i,0..2) pad]                 Fx[21:24, {9,10,11,15}], Fx[21:24,19:22]
+constexpr int FX2_NP = 74;   // 3x3 (+pad)  Fi[18:21,3:6]
+constexpr int FX2_NT = 84;   // 3x3 (+pad)  Fi[21:24,3:6]
+constexpr int FX2_SIZE = 94;
+constexpr int FX2_STRIDE = 94;
+
+// Filter._predict_nominal, IMU part (equations.py:72-86; state.py:62-69): p, v, q.
+//   R_WB   rot(q) of the pre-step quaternion;  Rn_out  = rot(q+) (the new R_WB_old, Filter.py:227)
+ESKF_HD void imu_nominal_step(double* p, double* v, double* q, const double* R_WB, double dt, const double* om_old,
+                              const double* acc_old, const double* om, const double* acc, double* R_new) {
+  double dth[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) dth[i] = dt * ((om_old[i] + om[i]) / 2.0);
+  double Rn[9], RS[9];
+  mul_skew(R_WB, dth, RS);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Rn[i] = R_WB[i] + RS[i];
+  double a0[3], a1[3];
+  mv3(R_WB, acc_old, a0);
+  mv3(Rn, acc, a1);
+  const double hdt2 = dt * dt / 2.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double aa = (a0[i] + a1[i]) / 2.0;
+    const double vi = v[i];
+    p[i] = p[i] + dt * vi + hdt2 * aa;
+    v[i] = vi + dt * aa;
+  }
+  quat_from_matrix(Rn, q);
+  quat_to_rot(q, R_new);
+}
+
+// Filter._predict_nominal, camera part (equations.py:88-98; state.py:70-74): p_cam, q_cam.
+//   v_pre, R_WB   pre-step IMU velocity and rotation;  pk/notch_d at the pre-step (dofs, notch)
+ESKF_HD void cam_nominal_step(double* pc, double* qc, const double* v_pre, const double* R_WB, double dt,
+                              const double* om_old, const double* om, const double* pk_p, const double* pk_R,
+                              const double* pk_z6, double notch_d) {
+  double om_avg[3], oxp[3], Roxp[3], omt[3], om_c[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) om_avg[i] = (om_old[i] + om[i]) / 2.0;
+  cross3(om_avg, pk_p, oxp);
+  mv3(R_WB, oxp, Roxp);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) omt[i] = om_old[i] + pk_z6[i] * notch_d;
+  mtv3(pk_R, omt, om_c);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) om_c[i] = dt * om_c[i];
+  double Rc[9], RcS[9];
+  quat_to_rot(qc, Rc);
+  mul_skew(Rc, om_c, RcS);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Rc[i] = Rc[i] + RcS[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) pc[i] = pc[i] + dt * v_pre[i] + dt * Roxp[i];
+  quat_from_matrix(Rc, qc);
+}
+
+// dofs / notch part of f_predict (equations.py:87; Filter.py:243-245).  Returns true when the probe
+// kinematics have to be re-evaluated (their inputs changed).
+ESKF_HD bool dofs_notch_step(const Model& m, double* dofs, double* notch, double dt) {
+  bool changed = false;
+  const double n0 = notch[0] + dt * notch[1];
+  const double n1 = notch[1] + dt * notch[2];
+  changed = (n0 != notch[0]);
+  notch[0] = n0;
+  notch[1] = n1;
+  if (m.flags & FLAG_ZERO_FROZEN) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if ((m.frozen_mask >> i) & 1) {
+        changed = changed || (dofs[i] != 0.0);
+        dofs[i] = 0.0;
+      }
+  }
+  return changed;
+}
+
+// Filter._predict_error (Filter.py:249-342): Jacobian blocks in the fx2 layout, from the buffered
+// R_old / om_old / acc_old and the POST-predict (dofs, notch) whose probe kinematics are (pk, t).
+ESKF_HD void jacobian_blocks(const Model& m, const double* dofs, double notch_d, const ProbeKin& pk, const ProbeTrig& t,
+                             const double* Ro, double dt, const double* om_old, const double* acc_old,
+                             const double* sig_om, bool want_noise_jac, double* fx) {
+  fx[FX2_DT] = dt;
+  {  // A = (-R_old [acc_old]x) dt
+    double T[9];
+    mul_skew(Ro, acc_old, T);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) fx[FX2_AB + 6 * i + k] = -T[3 * i + k] * dt;
+  }
+  {  // B = rot(normalise(quat(w=1, v=dt/2 om_old)))^T
+    double qo[4] = {0.5 * dt * om_old[0], 0.5 * dt * om_old[1], 0.5 * dt * om_old[2], 1.0};
+    quat_normalise(qo);
+    double Rb[9];
+    quat_to_rot(qo, Rb);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) fx[FX2_AB + 6 * i + 3 + j] = Rb[3 * j + i];
+  }
+  double wt[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) wt[i] = om_old[i] - sig_om[i];
+  {  // C1 = -dt R_old [w]x,  w = p + om_tr x p
+    double w[3], T[9];
+    cross3(wt, pk.p, w);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) w[i] = pk.p[i] + w[i];
+    mul_skew(Ro, w, T);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) fx[FX2_R18 + 10 * i + k] = -dt * T[3 * i + k];
+  }
+  {  // C2 = dt R_old (I + [om_tr]x) dp/dq(1..6)
+    double Mw[9], S[9];
+    mul_skew(Ro, wt, S);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Mw[i] = dt * (Ro[i] + S[i]);
+    const double lq = m.L - dofs[3];
+    const double dz2[3] = {t.s1 * t.s2, t.c1 * t.s2, t.c2};
+    const double k2 = dofs[4] * t.s3 + dofs[5] * t.c3;
+    double col[6][3];
+    col[0][0] = pk.p[1];
+    col[0][1] = -pk.p[0];
+    col[0][2] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      col[1][i] = lq * dz2[i] - k2 * pk.z6[i];
+      col[2][i] = dofs[4] * t.eb3[i] - dofs[5] * t.ea3[i];
+      col[3][i] = -pk.z6[i];
+      col[4][i] = t.ea3[i];
+      col[5][i] = t.eb3[i];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double y[3];
+      mv3(Mw, col[k], y);
+      fx[FX2_R18 + 0 * 10 + 3 + k] = y[0];
+      fx[FX2_R18 + 1 * 10 + 3 + k] = y[1];
+      fx[FX2_R18 + 2 * 10 + 3 + k] = y[2];
+    }
+  }
+  {  // D = dt d/dq{1,2,3,7} [ R(q)^T om_tr ]
+    const double al = dot3(t.ead, wt), be = dot3(t.ebd, wt), ze = dot3(pk.z6, wt);
+    const double al1 = t.ead[1] * wt[0] - t.ead[0] * wt[1];
+    const double be1 = t.ebd[1] * wt[0] - t.ebd[0] * wt[1];
+    const double ze1 = pk.z6[1] * wt[0] - pk.z6[0] * wt[1];
+    const double al2 = -t.sd * ze, be2 = -t.cd * ze, ze2 = t.sd * al + t.cd * be;
+    double* D0 = fx + FX2_R21;
+    double* D1 = fx + FX2_R21 + 8;
+    double* D2 = fx + FX2_R21 + 16;
+    D0[0] = dt * (-al1);
+    D1[0] = dt * (m.sa * ze1 + m.ca * be1);
+    D2[0] = dt * (m.ca * ze1 - m.sa * be1);
+    D0[1] = dt * (-al2);
+    D1[1] = dt * (m.sa * ze2 + m.ca * be2);
+    D2[1] = dt * (m.ca * ze2 - m.sa * be2);
+    D0[2] = dt * (-be);
+    D1[2] = dt * (-m.ca * al);
+    D2[2] = dt * (m.sa * al);
+    D0[3] = -D0[2];
+    D1[3] = -D1[2];
+    D2[3] = -D2[2];
+  }
+  {  // E = I - dt/2 [a + b]x
+    double ua[3], ub[3], a[3], b[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double omp = pk.z6[i] * notch_d;
+      ua[i] = wt[i] + omp;
+      ub[i] = om_old[i] + omp;
+    }
+    mtv3(pk.R, ua, a);
+    mtv3(pk.R, ub, b);
+    const double h = 0.5 * dt;
+    const double e0 = h * (a[0] + b[0]), e1 = h * (a[1] + b[1]), e2 = h * (a[2] + b[2]);
+    double* E0 = fx + FX2_R21 + 4;
+    double* E1 = fx + FX2_R21 + 8 + 4;
+    double* E2 = fx + FX2_R21 + 16 + 4;
+    E0[0] = 1.0;
+    E0[1] = e2;
+    E0[2] = -e1;
+    E1[0] = -e2;
+    E1[1] = 1.0;
+    E1[2] = e0;
+    E2[0] = e1;
+    E2[1] = -e0;
+    E2[2] = 1.0;
+  }
+  if (want_noise_jac) {
+    double T[9];
+    mul_skew(Ro, pk.p, T);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) fx[FX2_NP + i] = dt * T[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) fx[FX2_NT + 3 * i + j] = -dt * pk.R[3 * j + i];
+  }
+}
+
+// X <- Fx X for three 24-vectors held in registers (X[i][v] = element i of vector v): the sparse
+// transition matrix of Filter._predict_error applied as straight-line code.  Both covariance passes
+// of a step use this one function (column tile of P, then row tile of Fx P), see eskf_kernel2.cuh.
+// Coefficients come from the fx2 record through 16-byte loads.
+struct alignas(16) d2 {
+  double x, y;
+};
+// PS = stride between consecutive coefficient pairs of one record (1: plain array; F: the
+// [pair][filter] layout of the v2 kernel, conflict free for writer and readers).
+template <int PS>
+ESKF_HD double fx2_at(const d2* f2, int j) {
+  const d2 v = f2[(j >> 1) * PS];
+  return (j & 1) ? v.y : v.x;
+}
+template <int PS>
+ESKF_HD void fx_apply_reg(double (&X)[24][3], const d2* fx2) {
+  const d2* f2 = fx2;
+  const double dt = f2[(FX2_DT / 2) * PS].x;
+  double y18[3][3], y21[3][3];
+  // rows 18:21 (camera position error)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const d2 c0 = f2[((FX2_R18 + 10 * i) / 2 + 0) * PS], c1 = f2[((FX2_R18 + 10 * i) / 2 + 1) * PS], c2 = f2[((FX2_R18 + 10 * i) / 2 + 2) * PS],
+             c3 = f2[((FX2_R18 + 10 * i) / 2 + 3) * PS], c4 = f2[((FX2_R18 + 10 * i) / 2 + 4) * PS];
+    const double c[9] = {c0.x, c0.y, c1.x, c1.y, c2.x, c2.y, c3.x, c3.y, c4.x};
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      double y = dt * X[3 + i][v];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) y += c[k] * X[6 + k][v];  // C1 on theta (6:9), C2 on dofs (9:15)
+      y18[i][v] = y + X[16 + i][v];                          // mis-aligned identity block (quirk Q3)
+    }
+  }
+  // rows 21:24 (camera orientation error)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const d2 c0 = f2[((FX2_R21 + 8 * i) / 2 + 0) * PS], c1 = f2[((FX2_R21 + 8 * i) / 2 + 1) * PS], c2 = f2[((FX2_R21 + 8 * i) / 2 + 2) * PS],
+             c3 = f2[((FX2_R21 + 8 * i) / 2 + 3) * PS];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      double y = (i == 0) ? 0.0 : X[21 + i][v];  // Fx[22,22] = Fx[23,23] = 1
+      y += c0.x * X[9][v];
+      y += c0.y * X[10][v];
+      y += c1.x * X[11][v];
+      y += c1.y * X[15][v];
+      y += c2.x * X[19][v];
+      y += c2.y * X[20][v];
+      y += c3.x * X[21][v];
+      y21[i][v] = y;
+    }
+  }
+  // rows 0:3  p += dt v
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) X[i][v] = X[i][v] + dt * X[3 + i][v];
+  // rows 3:6  v += A theta ; rows 6:9  theta = B theta
+  {
+    double yt[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const d2 c0 = f2[((FX2_AB + 6 * i) / 2 + 0) * PS], c1 = f2[((FX2_AB + 6 * i) / 2 + 1) * PS], c2 = f2[((FX2_AB + 6 * i) / 2 + 2) * PS];
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        double yv = X[3 + i][v];
+        yv += c0.x * X[6][v];
+        yv += c0.y * X[7][v];
+        yv += c1.x * X[8][v];
+        X[3 + i][v] = yv;
+        double t = 0.0;
+        t += c1.y * X[6][v];
+        t += c2.x * X[7][v];
+        t += c2.y * X[8][v];
+        yt[i][v] = t;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int v = 0; v < 3; ++v) X[6 + i][v] = yt[i][v];
+  }
+  // rows 15:17 notch chain
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    X[15][v] = X[15][v] + dt * X[16][v];
+    X[16][v] = X[16][v] + dt * X[17][v];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      X[18 + i][v] = y18[i][v];
+      X[21 + i][v] = y21[i][v];
+    }
+}
+
+// Fi Q Fi^T for the row tile of lane group g (X[j][v] = P'[3g+v][j]); Filter.py:349.
+template <int PS, typename QD>
+ESKF_HD void process_noise_reg(double (&X)[24][3], int g, const d2* f2, const QD& qd, bool imu_q) {
+  // diagonal: rows 3..14 get qd[r-3] (Fi[3:15,0:12] = I), row 17 gets qd(12) (Fi[17,12] = 1)
+#pragma unroll
+  for (int r = 3; r < 15; ++r)
+    if (g == r / 3) X[r][r % 3] += qd(r - 3);
+  if (g == 5) X[17][2] += qd(12);
+  if (imu_q && (g == 2 || g == 6 || g == 7)) {
+    // n_om drives theta (I), p_C (Np) and theta_C (Nt): L Q_om L^T on rows/cols {6:9,18:21,21:24};
+    // the diagonal of the theta block was added above.
+    double Lr[3][3];
+#pragma unroll
+    for (int v = 0; v < 3; ++v)
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        Lr[v][k] = (g == 2) ? ((k == v) ? 1.0 : 0.0) : (g == 6) ? fx2_at<PS>(f2, FX2_NP + 3 * v + k) : fx2_at<PS>(f2, FX2_NT + 3 * v + k);
+#pragma unroll
+    for (int cb = 0; cb < 3; ++cb) {
+      const int c0 = (cb == 0) ? 6 : (cb == 1) ? 18 : 21;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double Lc[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          Lc[k] = (cb == 0) ? ((k == j) ? 1.0 : 0.0) : (cb == 1) ? fx2_at<PS>(f2, FX2_NP + 3 * j + k) : fx2_at<PS>(f2, FX2_NT + 3 * j + k);
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) acc += Lr[v][k] * qd(3 + k) * Lc[k];
+          if (!(g == 2 && cb == 0)) X[c0 + j][v] += acc;
+        }
+      }
+    }
+  }
+}
+
 }  // namespace eskf

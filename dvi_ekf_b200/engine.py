@@ -10,6 +10,7 @@ mirror the reference's ``Filter`` (dvi_ekf/filter/Filter.py): ``propagate``,
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -71,7 +72,7 @@ class BatchFilter:
 
     def __init__(self, n_filters: int, scope_length: float = 50.0, cam_angle_rad: float = np.deg2rad(30.0),
                  frozen_dofs: Sequence[int] = (1, 1, 1, 1, 1, 1), zero_frozen_dofs: bool = True, device: int = 0,
-                 stream: int = 0):
+                 stream: int = 0, variant: Optional[int] = None):
         self._lib = _lib.load()
         self.n = int(n_filters)
         self.device = int(device)
@@ -83,6 +84,10 @@ class BatchFilter:
         h = C.c_void_p()
         check(self._lib.eskf_create(C.byref(m), self.n, self.device, C.c_void_p(stream), C.byref(h)), "eskf_create")
         self._h = h
+        if variant is None:
+            variant = int(os.environ.get("ESKF_B200_VARIANT", "0"))
+        if variant:
+            self.set_variant(variant)
 
     # -- lifetime -----------------------------------------------------------
     def close(self):
@@ -232,6 +237,10 @@ class BatchFilter:
 
     def set_tuning(self, filters_per_cta: int = 0):
         check(self._lib.eskf_set_tuning(self._h, int(filters_per_cta)), "eskf_set_tuning")
+
+    def set_variant(self, variant: int = 0):
+        """0 = default kernel (warp-specialised v2), 1 = first kernel (v1), 2 = v2."""
+        check(self._lib.eskf_set_variant(self._h, int(variant)), "eskf_set_variant")
 
 
 def fp64_peak_tflops(device: int = 0, repeats: int = 5) -> float:

@@ -124,6 +124,9 @@ int eskf_sync(eskf_t* h);
 int64_t eskf_launch_count(const eskf_t* h);
 /* filters per CTA used for the kernels (tunable; 0 = automatic) */
 int eskf_set_tuning(eskf_t* h, int filters_per_cta);
+/* kernel variant: 0 = default (the warp-specialised eskf_kernel2), 1 = eskf_kernel (first version, kept for
+ * A/B measurements), 2 = eskf_kernel2 */
+int eskf_set_variant(eskf_t* h, int variant);
 
 /* Measurement aid (no reference counterpart): sustained FP64 FMA throughput of the device in
  * TFLOP/s (best of `repeats` launches of a pure DFMA kernel) -- the roofline denominator. */

@@ -72,4 +72,46 @@ int hc_update(const double* model, double* x, double* P, const double* u, const 
   return 1;
 }
 
+// The same step through the building blocks of the v2 kernel (eskf_kernel2.cuh): split scalar roles,
+// register tile X <- Fx X, transposition, X <- Fx X, process noise.
+void hc_propagate2(const double* model, double* x, double* P, double* u, double* Ro, double dt, const double* om_acc,
+                   const double* qd, const double* sig_om, double* fx_out) {
+  Model m{model[0], sin(model[1]), cos(model[1]), (int)model[2], (int)model[3]};
+  Nominal s; load_nominal(s, x, u, Ro);
+  ProbeKin pk; ProbeTrig t;
+  probe_eval(m, s.dofs, s.notch, pk, t);  // kinematics at the pre-step (dofs, notch)
+  double R_WB[9]; quat_to_rot(s.q, R_WB);
+  const bool imu_q = (qd[3] != 0.0) || (qd[4] != 0.0) || (qd[5] != 0.0);
+  // CAMERA role (pre-step v, R_WB, probe kinematics, notch')
+  cam_nominal_step(s.pc, s.qc, s.v, R_WB, dt, s.om_old, om_acc, pk.p, pk.R, pk.z6, s.notch[1]);
+  // JACOB role
+  alignas(16) double fx[FX2_SIZE];
+  for (int i = 0; i < FX2_SIZE; ++i) fx[i] = 0.0;
+  if (dofs_notch_step(m, s.dofs, s.notch, dt)) probe_eval(m, s.dofs, s.notch, pk, t);
+  jacobian_blocks(m, s.dofs, s.notch[1], pk, t, s.R_old, dt, s.om_old, s.acc_old, sig_om, imu_q, fx);
+  // IMU role
+  double Rn[9];
+  imu_nominal_step(s.p, s.v, s.q, R_WB, dt, s.om_old, s.acc_old, om_acc, om_acc + 3, Rn);
+  for (int i = 0; i < 9; ++i) s.R_old[i] = Rn[i];
+  for (int i = 0; i < 3; ++i) { s.om_old[i] = om_acc[i]; s.acc_old[i] = om_acc[3 + i]; }
+  // COVARIANCE role: eight lanes, tile of three columns each
+  const d2* f2 = reinterpret_cast<const d2*>(fx);
+  static double X[8][24][3];
+  double T[24][24];
+  for (int g = 0; g < 8; ++g) {
+    for (int i = 0; i < 24; ++i) for (int v = 0; v < 3; ++v) X[g][i][v] = P[i * 24 + 3 * g + v];
+    fx_apply_reg<1>(X[g], f2);
+    for (int i = 0; i < 24; ++i) for (int v = 0; v < 3; ++v) T[i][3 * g + v] = X[g][i][v];
+  }
+  auto qdf = [&](int j) { return qd[j]; };
+  for (int g = 0; g < 8; ++g) {
+    for (int k = 0; k < 24; ++k) for (int v = 0; v < 3; ++v) X[g][k][v] = T[3 * g + v][k];
+    fx_apply_reg<1>(X[g], f2);
+    process_noise_reg<1>(X[g], g, f2, qdf, imu_q);
+    for (int j = 0; j < 24; ++j) for (int v = 0; v < 3; ++v) P[(3 * g + v) * 24 + j] = X[g][j][v];
+  }
+  store_nominal(s, x, u, Ro);
+  if (fx_out) memcpy(fx_out, fx, sizeof(double) * FX2_SIZE);
+}
+
 }  // extern "C"

@@ -10,11 +10,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-9  # north-star: nominal state, error state and P within 1e-9 relative per step (FP64)
 
 
-@pytest.fixture(scope="module")
-def BatchFilter():
+@pytest.fixture(scope="module", params=[2, 1], ids=["kernel2", "kernel1"])
+def BatchFilter(request):
+    """the engine class bound to one kernel variant (2 = warp-specialised default, 1 = first kernel)"""
+    import functools
+
     from dvi_ekf_b200 import BatchFilter as BF
 
-    return BF
+    return functools.partial(BF, variant=request.param)
 
 
 def _setup(BF, sc, n, x=None, P=None, u=None, R_old=None, fpc=0):

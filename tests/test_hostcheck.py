@@ -1,0 +1,99 @@
+"""Device arithmetic on the CPU: dvi_ekf_b200/csrc/eskf_math.cuh compiled with g++ (tests/hostcheck) and
+replayed lane by lane, checked against the numpy oracle in lock-step at 1e-9 (norm-wise per state group /
+covariance block, tests/helpers.py).  Covers the first kernel's path (hc_propagate) and the building blocks of
+the warp-specialised kernel (hc_propagate2: split scalar roles, register tile, transposition)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import cov_err, mandala_scenario, random_filter_inputs, state_err
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-9
+dp = ctypes.POINTER(ctypes.c_double)
+
+
+def _p(a):
+    return a.ctypes.data_as(dp)
+
+
+@pytest.fixture(scope="module")
+def hc():
+    from dvi_ekf_b200 import build
+
+    lib = ctypes.CDLL(build.build_hostcheck())
+    for name in ("hc_propagate", "hc_propagate2"):
+        getattr(lib, name).argtypes = [dp, dp, dp, dp, dp, ctypes.c_double, dp, dp, dp, dp]
+        getattr(lib, name).restype = None
+    lib.hc_update.argtypes = [dp, dp, dp, dp, dp, dp, ctypes.c_double, dp, dp]
+    lib.hc_update.restype = ctypes.c_int
+    return lib
+
+
+def _model(cfg):
+    mask = sum(1 << i for i, f in enumerate(cfg.frozen_dofs) if f)
+    return np.array([cfg.length, cfg.angle, float(mask), 1.0 if cfg.zero_frozen_dofs else 0.0])
+
+
+@pytest.mark.parametrize("fn", ["hc_propagate", "hc_propagate2"])
+def test_lockstep_trajectory(hc, golden, fn):
+    sc = mandala_scenario(golden, n_frames=30, ifv=10)
+    kf = sc.new_oracle()
+    model = _model(sc.cfg)
+    step = getattr(hc, fn)
+    k = 0
+    ws = wP = 0.0
+    for e in range(len(sc.n_prop)):
+        for _ in range(sc.n_prop[e]):
+            x, P, u, Ro = [a.copy() for a in kf.get_vectors()]
+            kf.propagate(sc.dt[k], sc.om_acc[k, :3], sc.om_acc[k, 3:])
+            oa = sc.om_acc[k].copy()
+            step(_p(model), _p(x), _p(P), _p(u), _p(Ro), sc.dt[k], _p(oa), _p(sc.Qd), _p(sc.sig_om), None)
+            xr, Pr, ur, Rr = kf.get_vectors()
+            ws = max(ws, state_err(x, xr), np.abs(Ro - Rr).max(), np.abs(u - ur).max())
+            wP = max(wP, cov_err(P, Pr))
+            k += 1
+        x, P, u, Ro = [a.copy() for a in kf.get_vectors()]
+        K = kf.update(sc.cam_meas[e, :3], sc.cam_meas[e, 3:], sc.notch_meas[e])
+        cm = sc.cam_meas[e].copy()
+        Kd = np.zeros((24, 7))
+        assert hc.hc_update(_p(model), _p(x), _p(P), _p(u), _p(Ro), _p(cm), sc.notch_meas[e], _p(sc.Rd), _p(Kd)) == 1
+        xr, Pr, _, _ = kf.get_vectors()
+        ws = max(ws, state_err(x, xr))
+        wP = max(wP, cov_err(P, Pr, sc.Rd))
+        assert np.abs(Kd - K).max() / np.abs(K).max() < 1e-7
+    assert ws < TOL and wP < TOL, (ws, wP)
+
+
+@pytest.mark.parametrize("imu_q", [False, True])
+def test_v2_blocks_equal_v1_path_on_random_states(hc, golden, imu_q):
+    """hc_propagate2 (v2 building blocks) against hc_propagate (v1 path) and the oracle on random, non-frozen
+    states with non-zero notch rates; with and without IMU noise in Q (Filter.py:110-117)."""
+    sc = mandala_scenario(golden, n_frames=10, ifv=1, frozen_dofs=(0, 0, 0, 0, 0, 0))
+    rng = np.random.default_rng(7)
+    xs, Ps, us = random_filter_inputs(rng, 200, sc.cfg)
+    model = _model(sc.cfg)
+    qd = sc.Qd.copy()
+    if imu_q:
+        qd[0:6] = np.array([3e-4, 3e-4, 3e-4, 2e-5, 2e-5, 2e-5])
+    w12 = ws = wP = 0.0
+    for i in range(len(xs)):
+        dt = float(rng.uniform(0.01, 1.0))
+        oa = np.hstack((rng.normal(0, 0.05, 3), rng.normal(0, 0.5, 3)))
+        kf = sc.new_oracle(xs[i], Ps[i], us[i])
+        kf.Q = np.diag(qd)
+        x0, P0, u0, R0 = [a.copy() for a in kf.get_vectors()]
+        kf.propagate(dt, oa[:3], oa[3:])
+        xr, Pr, ur, Rr = kf.get_vectors()
+        outs = []
+        for fn in (hc.hc_propagate, hc.hc_propagate2):
+            x, P, u, Ro = x0.copy(), P0.copy(), u0.copy(), R0.copy()
+            fn(_p(model), _p(x), _p(P), _p(u), _p(Ro), dt, _p(oa.copy()), _p(qd), _p(sc.sig_om), None)
+            outs.append((x, P, u, Ro))
+            ws = max(ws, state_err(x, xr), np.abs(Ro - Rr).max())
+            wP = max(wP, cov_err(P, Pr))
+        w12 = max(w12, state_err(outs[1][0], outs[0][0]), cov_err(outs[1][1], outs[0][1]))
+    assert ws < TOL and wP < TOL, (ws, wP)
+    assert w12 < 1e-12, w12

@@ -1,0 +1,56 @@
+"""A/B timing of the kernel variants on the bench workload (CUDA events, one launch per pass).
+
+    python tools/variant_bench.py [--n 4096,32768] [--variants 1,2] [--fpc 0] [--reps 3]
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from bench import SEED, Workload, mc_initial_states  # noqa: E402
+from dvi_ekf_b200 import BatchFilter  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", default="4096,32768")
+    ap.add_argument("--variants", default="1,2")
+    ap.add_argument("--fpc", type=int, default=0)
+    ap.add_argument("--reps", type=int, default=3)
+    a = ap.parse_args()
+    wl = Workload()
+    s = wl.s
+    dev = torch.device("cuda")
+    t = lambda x, dt=torch.float64: torch.tensor(np.ascontiguousarray(x), dtype=dt, device=dev)
+    d = dict(dt=t(s.dt), oa=t(s.om_acc), npr=t(s.n_prop, torch.int32), cam=t(s.cam), notch=t(s.notch))
+    for N in [int(v) for v in a.n.split(",")]:
+        x0, P0, u0 = t(mc_initial_states(s.x0, N, 0)), t(wl.P0[None]), t(s.u0[None])
+        for var in [int(v) for v in a.variants.split(",")]:
+            for noise in (False, True):
+                bf = BatchFilter(N, variant=var, **wl.model)
+                bf.set_tuning(a.fpc)
+                bf.set_noise(wl.Qd[None], wl.Rd[None], wl.sig_om[None])
+                best = 1e9
+                for rep in range(a.reps):
+                    bf.set_state(x0, P0, u0, None)
+                    bf.sync()
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    kw = dict(imu_noise_std=wl.imu_std, cam_noise_std=wl.cam_std, seed=SEED) if noise else {}
+                    e0.record()
+                    bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], want_stats=False, **kw)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    best = min(best, e0.elapsed_time(e1))
+                print(f"variant={var} N={N} noise={noise}: {best:.3f} ms -> {N * len(s.dt) / best * 1e3:.3e} filter-steps/s",
+                      flush=True)
+                bf.close()
+
+
+if __name__ == "__main__":
+    main()
