@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(32 + 8 * F, 1) eskf_kernel(const __grid_consta
   // ---- scalar role state ----
   Nominal s;
   ProbeKin pk;
+  ProbeTrig ptr;
   bool after_update = true;  // R_WB must be recomputed from q (R_old may be stale, quirk Q8)
   int32_t st = 0;
   double sig_om[3] = {0, 0, 0};
@@ -217,8 +218,7 @@ __global__ void __launch_bounds__(32 + 8 * F, 1) eskf_kernel(const __grid_consta
 #pragma unroll
     for (int i = 0; i < 9; ++i) s.R_old[i] = rg[i];
     st = a.status[f0 + tid];
-    ProbeTrig t;
-    probe_eval(a.model, s.dofs, s.notch, pk, t);
+    probe_eval(a.model, s.dofs, s.notch, pk, ptr);
     const int64_t row = f0 + tid;
 #pragma unroll
     for (int i = 0; i < 3; ++i) sig_om[i] = a.par[row * PAR_STRIDE + PAR_SIGOM + i];
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(32 + 8 * F, 1) eskf_kernel(const __grid_consta
           }
           after_update = false;
 #ifndef ESKF_EXP_NO_SCALAR  // (profiling experiment switch: time the covariance role alone)
-          propagate_scalar(a.model, s, pk, Rq, dt, om, acc, sig_om, imu_q,
+          propagate_scalar(a.model, s, pk, ptr, Rq, dt, om, acc, sig_om, imu_q,
                            sScr + tid * SCR_STRIDE + (it & 1) * FX_STRIDE);
 #endif
         }
@@ -348,8 +348,7 @@ __global__ void __launch_bounds__(32 + 8 * F, 1) eskf_kernel(const __grid_consta
 #pragma unroll
           for (int i = 0; i < 24; ++i) d[i] = up[UP_DELTA + i];
           inject_error(a.model, s, d);
-          ProbeTrig t;
-          probe_eval(a.model, s.dofs, s.notch, pk, t);
+          probe_eval(a.model, s.dofs, s.notch, pk, ptr);
           after_update = true;
           n_upd += 1.0;
         } else {

@@ -31,6 +31,18 @@
 #pragma once
 #include "eskf_kernel.cuh"
 
+// profiling experiment switches (python -m dvi_ekf_b200.build --exp=...): time one side of the kernel alone
+#ifdef ESKF_EXP_NO_SCALAR
+#define ESKF2_SCALAR_ON(it) ((it) < 2)  // scalar roles only fill both record slots once per epoch
+#else
+#define ESKF2_SCALAR_ON(it) true
+#endif
+#ifdef ESKF_EXP_NO_COV
+#define ESKF2_COV_ON false
+#else
+#define ESKF2_COV_ON true
+#endif
+
 namespace eskf {
 
 constexpr int RS2 = 26;          // row stride of the covariance tile buffer: even (16-byte rows) and
@@ -165,7 +177,7 @@ __device__ __forceinline__ void role_imu(const KArgs& a, const Ctx2& c, int lane
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
     for (int it = 0; it <= n; ++it) {
-      if (act && it < n) {
+      if (act && it < n && ESKF2_SCALAR_ON(it)) {
         const int64_t kk = k + it;
         const double* uo = sx + (SX_RING + 8 * (int)(kk & 3)) * F;
         const double* un = sx + (SX_RING + 8 * (int)((kk + 1) & 3)) * F;
@@ -280,7 +292,7 @@ __device__ __forceinline__ void role_cam(const KArgs& a, const Ctx2& c, int lane
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
     for (int it = 0; it <= n; ++it) {
-      if (act && it < n) {
+      if (act && it < n && ESKF2_SCALAR_ON(it)) {
         const int64_t kk = k + it;
         const double* uo = sx + (SX_RING + 8 * (int)(kk & 3)) * F;
         const double* un = sx + (SX_RING + 8 * (int)((kk + 1) & 3)) * F;
@@ -422,7 +434,7 @@ __device__ __forceinline__ void role_jac(const KArgs& a, const Ctx2& c, int lane
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
     for (int it = 0; it <= n; ++it) {
-      if (act && it < n) {
+      if (act && it < n && ESKF2_SCALAR_ON(it)) {
         const int64_t kk = k + it;
         const double* uo = sx + (SX_RING + 8 * (int)(kk & 3)) * F;
         const double dt = sx[(SX_RING + 8 * (int)((kk + 1) & 3) + 6) * F];
@@ -561,7 +573,7 @@ __device__ __forceinline__ void role_stage(const KArgs& a, const Ctx2& c, int la
     for (int it = 0; it <= n; ++it) {
       if (act) {
         if (it == 0 && a.do_update) stage_meas(e);
-        if (it < n && k + it + 1 < a.T) stage_sample(k + it + 1);
+        if (it < n && k + it + 1 < a.T && ESKF2_SCALAR_ON(it)) stage_sample(k + it + 1);
       }
       __syncthreads();
     }
@@ -621,23 +633,15 @@ __device__ __forceinline__ void role_cov(const KArgs& a, const Ctx2& c, int ct) 
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
     for (int it = 0; it <= n; ++it) {
-      if (it >= 1) {
+      if (it >= 1 && ESKF2_COV_ON) {
         const d2* f2 = fxb + (((it - 1) & 1) * NPAIR) * F;
-        // one copy of the Fx code serves both passes (instruction-cache footprint)
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-          // pass 0: T(:, 3g..3g+2) = Fx P(:, 3g..3g+2);  pass 1: P'(3g+v, :) = Fx T(3g+v, :)^T
-          fx_apply_reg<F>(X, f2);
-          if (pass == 0) {
-#pragma unroll
-            for (int i = 0; i < 24; ++i)
-#pragma unroll
-              for (int v = 0; v < 3; ++v) Tb[i * RS2 + 3 * cg + v] = X[i][v];
-            __syncwarp(gmask);
-            load_rows();  // X[k][v] = T(3g+v, k)
-            __syncwarp(gmask);
-          }
-        }
+        // pass 1: T(:, 3g..3g+2) = Fx P(:, 3g..3g+2), rows stored as they are finished
+        fx_apply_store<F, RS2>(X, f2, Tb + 3 * cg);
+        __syncwarp(gmask);
+        load_rows();  // X[k][v] = T(3g+v, k)
+        __syncwarp(gmask);
+        // pass 2: P'(3g+v, :) = Fx T(3g+v, :)^T
+        fx_apply_reg<F>(X, f2);
         process_noise_reg<F>(X, cg, f2, qd, imu_q);
       }
       __syncthreads();

@@ -143,12 +143,13 @@ ESKF_HD void quat_to_rot(const double* q, double* R) {
 // Quaternion.normalise (Quaternion.py:195-206): divide by the norm, force w >= 0.
 ESKF_HD void quat_normalise(double* q) {
   const double d = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  const double s = (q[3] < 0.0) ? -1.0 : 1.0;
-  // (q / d) then sign flip: the flip is exact, so fold it into the quotient
-  q[0] = s * (q[0] / d);
-  q[1] = s * (q[1] / d);
-  q[2] = s * (q[2] / d);
-  q[3] = s * (q[3] / d);
+  // q / d as q * (1 / d): one division instead of four (<= 1 ulp from the reference's quotient, far
+  // inside the 1e-9 budget); the sign flip is exact and folded into the factor
+  const double r = ((q[3] < 0.0) ? -1.0 : 1.0) / d;
+  q[0] = q[0] * r;
+  q[1] = q[1] * r;
+  q[2] = q[2] * r;
+  q[3] = q[3] * r;
 }
 
 // Quaternion(val=M, do_normalise=True): scipy-1.10.1 Rotation.from_matrix
@@ -256,13 +257,33 @@ ESKF_HD void probe_eval(const Model& m, const double* dofs, const double* notch,
   }
 }
 
+// dofs / notch part of f_predict (equations.py:87; Filter.py:243-245).  Returns true when the probe
+// kinematics have to be re-evaluated (their inputs changed).
+ESKF_HD bool dofs_notch_step(const Model& m, double* dofs, double* notch, double dt) {
+  bool changed = false;
+  const double n0 = notch[0] + dt * notch[1];
+  const double n1 = notch[1] + dt * notch[2];
+  changed = (n0 != notch[0]);
+  notch[0] = n0;
+  notch[1] = n1;
+  if (m.flags & FLAG_ZERO_FROZEN) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if ((m.frozen_mask >> i) & 1) {
+        changed = changed || (dofs[i] != 0.0);
+        dofs[i] = 0.0;
+      }
+  }
+  return changed;
+}
+
 // ---- propagate: nominal state + Jacobian blocks -------------------------------------
 // One Filter.propagate (Filter.py:219-230) minus the covariance product.
 //   s        in: pre-step state and buffers; out: post-step state and buffers
-//   pk       in: probe kinematics at the pre-step (dofs, notch); out: at the post-step ones
+//   pk, t    in: probe kinematics at the pre-step (dofs, notch); out: at the post-step ones
 //   R_WB     rot(q) of the pre-step quaternion (== s.R_old unless an update intervened)
 //   fx       out: Jacobian blocks (FX_* layout)
-ESKF_HD void propagate_scalar(const Model& m, Nominal& s, ProbeKin& pk, const double* R_WB, double dt,
+ESKF_HD void propagate_scalar(const Model& m, Nominal& s, ProbeKin& pk, ProbeTrig& t, const double* R_WB, double dt,
                               const double* om, const double* acc, const double* sig_om, bool want_noise_jac,
                               double* fx) {
   // ---- f_predict (equations.py:44-50,72-100) with the pre-step state ----
@@ -307,21 +328,14 @@ ESKF_HD void propagate_scalar(const Model& m, Nominal& s, ProbeKin& pk, const do
     s.p[i] = s.p[i] + dt * vi + hdt2 * acc_avg[i];
     s.v[i] = vi + dt * acc_avg[i];
   }
-  s.notch[0] = s.notch[0] + dt * s.notch[1];
-  s.notch[1] = s.notch[1] + dt * s.notch[2];
-  if (m.flags & FLAG_ZERO_FROZEN) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-      if ((m.frozen_mask >> i) & 1) s.dofs[i] = 0.0;
-  }
+  const bool probe_changed = dofs_notch_step(m, s.dofs, s.notch, dt);
   // State.from_array (state.py:62-74): Markley quaternions of the first-order matrices
   quat_from_matrix(Rn, s.q);
   quat_from_matrix(Rc, s.qc);
 
   // ---- error Jacobians (Filter.py:249-342) with the buffered R_old / om_old / acc_old
   //      and the POST-predict dofs / notch ----
-  ProbeTrig t;
-  probe_eval(m, s.dofs, s.notch, pk, t);
+  if (probe_changed) probe_eval(m, s.dofs, s.notch, pk, t);  // (pk, t) persist: same inputs, same kinematics
   const double* Ro = s.R_old;
   fx[FX_DT] = dt;
   {  // A = (-R_old [acc_old]x) dt
@@ -933,26 +947,6 @@ ESKF_HD void cam_nominal_step(double* pc, double* qc, const double* v_pre, const
   quat_from_matrix(Rc, qc);
 }
 
-// dofs / notch part of f_predict (equations.py:87; Filter.py:243-245).  Returns true when the probe
-// kinematics have to be re-evaluated (their inputs changed).
-ESKF_HD bool dofs_notch_step(const Model& m, double* dofs, double* notch, double dt) {
-  bool changed = false;
-  const double n0 = notch[0] + dt * notch[1];
-  const double n1 = notch[1] + dt * notch[2];
-  changed = (n0 != notch[0]);
-  notch[0] = n0;
-  notch[1] = n1;
-  if (m.flags & FLAG_ZERO_FROZEN) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-      if ((m.frozen_mask >> i) & 1) {
-        changed = changed || (dofs[i] != 0.0);
-        dofs[i] = 0.0;
-      }
-  }
-  return changed;
-}
-
 // Filter._predict_error (Filter.py:249-342): Jacobian blocks in the fx2 layout, from the buffered
 // R_old / om_old / acc_old and the POST-predict (dofs, notch) whose probe kinematics are (pk, t).
 ESKF_HD void jacobian_blocks(const Model& m, const double* dofs, double notch_d, const ProbeKin& pk, const ProbeTrig& t,
@@ -1173,6 +1167,93 @@ ESKF_HD void fx_apply_reg(double (&X)[24][3], const d2* fx2) {
       X[18 + i][v] = y18[i][v];
       X[21 + i][v] = y21[i][v];
     }
+}
+
+// Pass 1 of a covariance step: T(:, tile) = Fx X, every finished row stored straight away as
+// out[i * OS + v] (no in-place update: X is dead after this pass, the next pass starts from the
+// transposed tile).  Interleaving the 72 stores with the FMAs lets the shared-memory pipe and the FP64
+// pipe overlap inside one warp.
+template <int PS, int OS>
+ESKF_HD void fx_apply_store(const double (&X)[24][3], const d2* f2, double* out) {
+  const double dt = f2[(FX2_DT / 2) * PS].x;
+  // untouched rows (identity rows of Fx): dofs 9:15 and notch'' 17
+#pragma unroll
+  for (int i = 9; i < 15; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) out[i * OS + v] = X[i][v];
+#pragma unroll
+  for (int v = 0; v < 3; ++v) out[17 * OS + v] = X[17][v];
+  // rows 18:21 (camera position error)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const d2 c0 = f2[((FX2_R18 + 10 * i) / 2 + 0) * PS], c1 = f2[((FX2_R18 + 10 * i) / 2 + 1) * PS],
+             c2 = f2[((FX2_R18 + 10 * i) / 2 + 2) * PS], c3 = f2[((FX2_R18 + 10 * i) / 2 + 3) * PS],
+             c4 = f2[((FX2_R18 + 10 * i) / 2 + 4) * PS];
+    const double c[9] = {c0.x, c0.y, c1.x, c1.y, c2.x, c2.y, c3.x, c3.y, c4.x};
+    double y[3];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) y[v] = dt * X[3 + i][v];
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+      for (int v = 0; v < 3; ++v) y[v] += c[k] * X[6 + k][v];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) out[(18 + i) * OS + v] = y[v] + X[16 + i][v];
+  }
+  // rows 21:24 (camera orientation error)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const d2 c0 = f2[((FX2_R21 + 8 * i) / 2 + 0) * PS], c1 = f2[((FX2_R21 + 8 * i) / 2 + 1) * PS],
+             c2 = f2[((FX2_R21 + 8 * i) / 2 + 2) * PS], c3 = f2[((FX2_R21 + 8 * i) / 2 + 3) * PS];
+    double y[3];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      y[v] = (i == 0) ? 0.0 : X[21 + i][v];
+      y[v] += c0.x * X[9][v];
+    }
+#pragma unroll
+    for (int v = 0; v < 3; ++v) y[v] += c0.y * X[10][v];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) y[v] += c1.x * X[11][v];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) y[v] += c1.y * X[15][v];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) y[v] += c2.x * X[19][v];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) y[v] += c2.y * X[20][v];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) out[(21 + i) * OS + v] = y[v] + c3.x * X[21][v];
+  }
+  // rows 0:3  p += dt v
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) out[i * OS + v] = X[i][v] + dt * X[3 + i][v];
+  // rows 3:6  v += A theta ; rows 6:9  theta = B theta
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const d2 c0 = f2[((FX2_AB + 6 * i) / 2 + 0) * PS], c1 = f2[((FX2_AB + 6 * i) / 2 + 1) * PS],
+             c2 = f2[((FX2_AB + 6 * i) / 2 + 2) * PS];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      double yv = X[3 + i][v];
+      yv += c0.x * X[6][v];
+      yv += c0.y * X[7][v];
+      yv += c1.x * X[8][v];
+      out[(3 + i) * OS + v] = yv;
+      double t = 0.0;
+      t += c1.y * X[6][v];
+      t += c2.x * X[7][v];
+      t += c2.y * X[8][v];
+      out[(6 + i) * OS + v] = t;
+    }
+  }
+  // rows 15:17 notch chain
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    out[15 * OS + v] = X[15][v] + dt * X[16][v];
+    out[16 * OS + v] = X[16][v] + dt * X[17][v];
+  }
 }
 
 // Fi Q Fi^T for the row tile of lane group g (X[j][v] = P'[3g+v][j]); Filter.py:349.

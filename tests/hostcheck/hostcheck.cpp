@@ -31,7 +31,7 @@ void hc_propagate(const double* model, double* x, double* P, double* u, double* 
   double R_WB[9]; quat_to_rot(s.q, R_WB);
   double fx[FX_STRIDE];
   const bool imu_q = (qd[3] != 0.0) || (qd[4] != 0.0) || (qd[5] != 0.0);
-  propagate_scalar(m, s, pk, R_WB, dt, om_acc, om_acc + 3, sig_om, imu_q, fx);
+  propagate_scalar(m, s, pk, t, R_WB, dt, om_acc, om_acc + 3, sig_om, imu_q, fx);
   constexpr int RS = 25;
   double Ps[24 * RS];
   for (int i = 0; i < 24; ++i) for (int j = 0; j < 24; ++j) Ps[i * RS + j] = P[i * 24 + j];
@@ -100,8 +100,7 @@ void hc_propagate2(const double* model, double* x, double* P, double* u, double*
   double T[24][24];
   for (int g = 0; g < 8; ++g) {
     for (int i = 0; i < 24; ++i) for (int v = 0; v < 3; ++v) X[g][i][v] = P[i * 24 + 3 * g + v];
-    fx_apply_reg<1>(X[g], f2);
-    for (int i = 0; i < 24; ++i) for (int v = 0; v < 3; ++v) T[i][3 * g + v] = X[g][i][v];
+    fx_apply_store<1, 24>(X[g], f2, &T[0][0] + 3 * g);
   }
   auto qdf = [&](int j) { return qd[j]; };
   for (int g = 0; g < 8; ++g) {
