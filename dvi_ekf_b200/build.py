@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libeskf_b200.so")
 SHAPES = (4, 8, 12, 16, 20, 24, 28)  # filters per CTA of eskf_kernel (v1); keep in sync with eskf_api.cu
-SHAPES2 = (4, 8, 16, 28)  # filters per CTA of eskf_kernel2 (v2)
+SHAPES3 = (4, 8, 16, 28)  # filters per CTA of eskf_kernel3 (v3)
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
@@ -58,16 +58,16 @@ def build_cuda(force: bool = False, verbose: bool = False, defines=(), suffix: s
         LIB = os.path.join(HERE, f"libeskf_b200{suffix}.so")
     extra = [f"-D{d}" for d in defines]
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, h) for h in ("eskf_math.cuh", "eskf_rng.cuh", "eskf_kernel.cuh", "eskf_kernel2.cuh")]
+    headers = [os.path.join(CSRC, h) for h in ("eskf_math.cuh", "eskf_rng.cuh", "eskf_kernel.cuh", "eskf_cov3.cuh", "eskf_kernel3.cuh")]
     headers.append(os.path.join(ROOT, "include", "eskf.h"))
     jobs = []
     for f in SHAPES:
         obj = os.path.join(OBJ, f"eskf_launch_f{f}.o")
         src = os.path.join(CSRC, "eskf_launch.cu")
         jobs.append((obj, [src] + headers, [_nvcc(), *NVCC_FLAGS, *extra, f"-DESKF_F={f}", "-c", src, "-o", obj]))
-    for f in SHAPES2:
-        obj = os.path.join(OBJ, f"eskf_launch2_f{f}.o")
-        src = os.path.join(CSRC, "eskf_launch2.cu")
+    for f in SHAPES3:
+        obj = os.path.join(OBJ, f"eskf_launch3_f{f}.o")
+        src = os.path.join(CSRC, "eskf_launch3.cu")
         jobs.append((obj, [src] + headers, [_nvcc(), *NVCC_FLAGS, *extra, f"-DESKF_F={f}", "-c", src, "-o", obj]))
     api_obj = os.path.join(OBJ, "eskf_api.o")
     api_src = os.path.join(CSRC, "eskf_api.cu")
@@ -87,7 +87,7 @@ def build_cuda(force: bool = False, verbose: bool = False, defines=(), suffix: s
 def build_hostcheck(force: bool = False) -> str:
     src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp")
     lib = os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so")
-    deps = [src, os.path.join(CSRC, "eskf_math.cuh"), os.path.join(CSRC, "eskf_rng.cuh")]
+    deps = [src, os.path.join(CSRC, "eskf_math.cuh"), os.path.join(CSRC, "eskf_rng.cuh"), os.path.join(CSRC, "eskf_cov3.cuh")]
     if force or not _newer(lib, deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", lib, src], check=True)
     return lib
@@ -96,7 +96,7 @@ def build_hostcheck(force: bool = False) -> str:
 def ptxas_summary() -> str:
     """registers / spills / shared memory per kernel, from the saved nvcc logs."""
     lines = []
-    for tag, shapes in (("", SHAPES), ("2", SHAPES2)):
+    for tag, shapes in (("", SHAPES), ("3", SHAPES3)):
         for f in shapes:
             log = os.path.join(OBJ, f"eskf_launch{tag}_f{f}.o.log")
             if os.path.exists(log):

@@ -8,7 +8,7 @@
 
 #include <string>
 
-#include "eskf_kernel2.cuh"
+#include "eskf_kernel3.cuh"
 
 using namespace eskf;
 
@@ -16,9 +16,9 @@ namespace eskf {
 #define ESKF_DECL(F) template <> cudaError_t launch_eskf_kernel<F>(const KArgs& a, cudaStream_t stream);
 ESKF_DECL(4) ESKF_DECL(8) ESKF_DECL(12) ESKF_DECL(16) ESKF_DECL(20) ESKF_DECL(24) ESKF_DECL(28)
 #undef ESKF_DECL
-#define ESKF_DECL2(F) template <> cudaError_t launch_eskf_kernel2<F>(const KArgs& a, cudaStream_t stream);
-ESKF_DECL2(4) ESKF_DECL2(8) ESKF_DECL2(16) ESKF_DECL2(28)
-#undef ESKF_DECL2
+#define ESKF_DECL3(F) template <> cudaError_t launch_eskf_kernel3<F>(const KArgs& a, cudaStream_t stream);
+ESKF_DECL3(4) ESKF_DECL3(8) ESKF_DECL3(16) ESKF_DECL3(28)
+#undef ESKF_DECL3
 }  // namespace eskf
 
 namespace {
@@ -86,7 +86,7 @@ struct eskf_handle {
   double* stats_sum_dev = nullptr;
   int64_t launches = 0;
   int fpc = 0;  // filters per CTA (0 = automatic)
-  int variant = 0;  // 0 = default (v2), 1 = eskf_kernel (v1), 2 = eskf_kernel2 (v2)
+  int variant = 0;  // 0 = default (eskf_kernel3), 1 = eskf_kernel (first version, kept for A/B measurements), 3 = eskf_kernel3
   int sm_count = 148;
 };
 
@@ -125,9 +125,9 @@ static int stage_in(eskf_t* h, int slot, const void* src, size_t bytes, int mem,
 }
 
 static const int kShapes1[] = {28, 24, 20, 16, 12, 8, 4};  // eskf_kernel  (v1)
-static const int kShapes2[] = {28, 16, 8, 4};              // eskf_kernel2 (v2)
+static const int kShapes3[] = {28, 16, 8, 4};              // eskf_kernel3
 
-static bool use_v2(const eskf_t* h) { return h->variant != 1; }
+static int kernel_of(const eskf_t* h) { return h->variant == 1 ? 1 : 3; }
 
 // Filters per CTA.  Must divide filters_per_traj when several trajectories are stacked (a CTA follows
 // ONE trajectory's epoch structure).  Every shape runs one CTA per SM (registers / shared memory) and a
@@ -135,8 +135,8 @@ static bool use_v2(const eskf_t* h) { return h->variant != 1; }
 // automatic choice minimises the number of waves and then prefers the larger shape.
 static int pick_fpc(const eskf_t* h, int64_t fpt, bool multi_traj) {
   auto fits = [&](int c) { return !multi_traj || (fpt % c) == 0; };
-  const int* shapes = use_v2(h) ? kShapes2 : kShapes1;
-  const int ns = use_v2(h) ? 4 : 7;
+  const int* shapes = kernel_of(h) == 3 ? kShapes3 : kShapes1;
+  const int ns = kernel_of(h) == 3 ? 4 : 7;
   if (h->fpc > 0) {
     for (int i = 0; i < ns; ++i)
       if (shapes[i] == h->fpc && fits(shapes[i])) return shapes[i];
@@ -159,12 +159,12 @@ static int pick_fpc(const eskf_t* h, int64_t fpt, bool multi_traj) {
 static int launch(eskf_t* h, const KArgs& a, int64_t fpt, bool multi_traj) {
   cudaError_t e;
   const int fpc = pick_fpc(h, fpt, multi_traj);
-  if (use_v2(h)) {
+  if (kernel_of(h) == 3) {
     switch (fpc) {
-      case 28: e = launch_eskf_kernel2<28>(a, h->stream); break;
-      case 16: e = launch_eskf_kernel2<16>(a, h->stream); break;
-      case 8: e = launch_eskf_kernel2<8>(a, h->stream); break;
-      case 4: e = launch_eskf_kernel2<4>(a, h->stream); break;
+      case 28: e = launch_eskf_kernel3<28>(a, h->stream); break;
+      case 16: e = launch_eskf_kernel3<16>(a, h->stream); break;
+      case 8: e = launch_eskf_kernel3<8>(a, h->stream); break;
+      case 4: e = launch_eskf_kernel3<4>(a, h->stream); break;
       default:
         g_err = "filters_per_traj must be a multiple of 4 when several trajectories are stacked";
         return ESKF_EINVAL;
@@ -519,7 +519,7 @@ int eskf_fp64_peak(int device, void* cuda_stream, int repeats, double* tflops_ou
 int64_t eskf_launch_count(const eskf_t* h) { return h ? h->launches : 0; }
 
 int eskf_set_variant(eskf_t* h, int variant) {
-  if (!h || variant < 0 || variant > 2) return ESKF_EINVAL;
+  if (!h || (variant != 0 && variant != 1 && variant != 3)) return ESKF_EINVAL;
   h->variant = variant;
   return ESKF_OK;
 }

@@ -1,0 +1,417 @@
+// Covariance algebra of the VI-ESKF hot path on a REGISTER-RESIDENT tile (FP64), the building blocks of
+// the covariance role of eskf_kernel3.cuh.  Host/device straight-line code: tests/hostcheck replays the
+// eight lanes of a filter on the CPU against the oracle.
+//
+// Eight lanes own one filter; lane g keeps X[k][v] = P(k, 3g+v), the three columns of state group g of
+// the symmetric 24x24 covariance (72 doubles).
+//   Filter._predict_error_covariance (Filter.py:344-349):   P' = Fx P Fx^T + Fi Q Fi^T
+//       pass 1   T(:, tile) = Fx X                   local; rows go straight to the transposition buffer
+//       transposition through shared memory          X[k][v] <- T(3g+v, k)
+//       pass 2   X <- Fx X (+ Q terms)               = (Fx T^T)(:, tile) = P'(tile, :)^T = P'(:, tile)
+//   Filter.update (Filter.py:351-395), all on the register tile:
+//       S columns live in lanes 5..7 (H selects rows/cols {18..23, 15}); K rows use P(h_m, r) = X[h_m][v];
+//       W = (I - K H) P is local given K; P' = W (I - K H)^T + (K R) K^T needs W(:, h) and K R; the reset blocks
+//       G = I - [delta_theta / 2]x mix rows 6:9 / 21:24 (local) and the columns of lanes 2 and 7 (local).
+// The sparse transition matrix is applied with nine (three rows x three columns) independent accumulators
+// per row group so that the FP64 pipe always has independent work in flight.
+#pragma once
+#include "eskf_math.cuh"
+
+namespace eskf {
+
+// N consecutive coefficients starting at the (even) record offset BASE, held as pairs
+template <int PS, int BASE, int N>
+struct Coefs {
+  d2 p[(N + 1) / 2];
+  ESKF_HD void load(const d2* f2) {
+#pragma unroll
+    for (int j = 0; j < (N + 1) / 2; ++j) p[j] = f2[(BASE / 2 + j) * PS];
+  }
+  ESKF_HD double operator()(int idx) const { return (idx & 1) ? p[idx >> 1].y : p[idx >> 1].x; }
+};
+
+// rows 21:24 (camera orientation error): y[i][v]
+template <int PS>
+ESKF_HD void fx3_rows_h2(const double (&X)[24][3], const d2* f2, double (&y)[3][3]) {
+  Coefs<PS, FX3_H2, 21> c;
+  c.load(f2);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) y[i][v] = (i == 0) ? 0.0 : X[21 + i][v];  // Fx[22,22] = Fx[23,23] = 1
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int col = (k < 3) ? 9 + k : (k == 3) ? 15 : 19 + (k - 4);  // D on dofs 1..3 and the notch, E on 19:22 (quirk Q3)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int v = 0; v < 3; ++v) y[i][v] += c(3 * k + i) * X[col][v];
+  }
+}
+
+// rows 18:21 (camera position error): y[i][v]
+template <int PS>
+ESKF_HD void fx3_rows_h1(const double (&X)[24][3], const d2* f2, double dt, double (&y)[3][3]) {
+  Coefs<PS, FX3_H1, 27> c;
+  c.load(f2);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) y[i][v] = X[16 + i][v] + dt * X[3 + i][v];  // mis-aligned identity block (quirk Q3)
+#pragma unroll
+  for (int k = 0; k < 9; ++k)  // C1 on theta (6:9), C2 on dofs (9:15)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int v = 0; v < 3; ++v) y[i][v] += c(3 * k + i) * X[6 + k][v];
+}
+
+// rows 3:6  v += A theta ; rows 6:9  theta = B theta
+template <int PS>
+ESKF_HD void fx3_rows_ab(const double (&X)[24][3], const d2* f2, double (&ya)[3][3], double (&yb)[3][3]) {
+  Coefs<PS, FX3_AB, 18> c;
+  c.load(f2);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      ya[i][v] = X[3 + i][v];
+      yb[i][v] = 0.0;
+    }
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        ya[i][v] += c(6 * k + i) * X[6 + k][v];
+        yb[i][v] += c(6 * k + 3 + i) * X[6 + k][v];
+      }
+}
+
+// Pass 1: T(:, tile) = Fx X, row i stored as out[i * OS + v] as soon as it is finished (X is not modified;
+// the next pass starts from the transposed tile).
+template <int PS, int OS>
+ESKF_HD void fx3_apply_store(const double (&X)[24][3], const d2* f2, double* out) {
+  const double dt = f2[(FX3_DT / 2) * PS].x;
+  // identity rows of Fx: dofs 9:15 and notch'' 17
+#pragma unroll
+  for (int i = 9; i < 15; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) out[i * OS + v] = X[i][v];
+#pragma unroll
+  for (int v = 0; v < 3; ++v) out[17 * OS + v] = X[17][v];
+  double y[3][3], z[3][3];
+  fx3_rows_h2<PS>(X, f2, y);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) out[(21 + i) * OS + v] = y[i][v];
+  fx3_rows_h1<PS>(X, f2, dt, y);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) out[(18 + i) * OS + v] = y[i][v];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)  // rows 0:3  p += dt v
+#pragma unroll
+    for (int v = 0; v < 3; ++v) out[i * OS + v] = X[i][v] + dt * X[3 + i][v];
+  fx3_rows_ab<PS>(X, f2, y, z);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      out[(3 + i) * OS + v] = y[i][v];
+      out[(6 + i) * OS + v] = z[i][v];
+    }
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {  // rows 15:17 notch chain
+    out[15 * OS + v] = X[15][v] + dt * X[16][v];
+    out[16 * OS + v] = X[16][v] + dt * X[17][v];
+  }
+}
+
+// Pass 2: X <- Fx X in place.
+template <int PS>
+ESKF_HD void fx3_apply_inplace(double (&X)[24][3], const d2* f2) {
+  const double dt = f2[(FX3_DT / 2) * PS].x;
+  double y21[3][3], y18[3][3], ya[3][3], yb[3][3];
+  fx3_rows_h2<PS>(X, f2, y21);
+  fx3_rows_h1<PS>(X, f2, dt, y18);  // reads X[18] (row 20), so rows 18:21 are assigned after it
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      X[21 + i][v] = y21[i][v];
+      X[18 + i][v] = y18[i][v];
+      X[i][v] = X[i][v] + dt * X[3 + i][v];
+    }
+  fx3_rows_ab<PS>(X, f2, ya, yb);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      X[3 + i][v] = ya[i][v];
+      X[6 + i][v] = yb[i][v];
+    }
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    X[15][v] = X[15][v] + dt * X[16][v];
+    X[16][v] = X[16][v] + dt * X[17][v];
+  }
+}
+
+// this lane's share of the diagonal of Fi Q Fi^T: rows 3..14 get qd[r-3] (Fi[3:15,0:12] = I), row 17 gets
+// qd[12] (Fi[17,12] = 1); qdv[v] belongs to row 3g+v.  qd(j) = diag(Q)[j].
+template <typename QD>
+ESKF_HD void fx3_noise_diag(int g, const QD& qd, double (&qdv)[3]) {
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    const int r = 3 * g + v;
+    qdv[v] = (r >= 3 && r < 15) ? qd(r - 3) : (r == 17) ? qd(12) : 0.0;
+  }
+}
+
+// Fi Q Fi^T for the tile of lane group g (Filter.py:349).
+template <int PS, typename QD>
+ESKF_HD void fx3_process_noise(double (&X)[24][3], int g, const d2* f2, const double (&qdv)[3], const QD& qd, bool imu_q) {
+  // diagonal entries P'(3g+v, 3g+v) = X[3g+v][v]: branch-free selects, every index is a constant
+#pragma unroll
+  for (int j = 1; j < 5; ++j)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) X[3 * j + v][v] += (g == j) ? qdv[v] : 0.0;
+  X[17][2] += (g == 5) ? qdv[2] : 0.0;
+  if (imu_q && (g == 2 || g == 6 || g == 7)) {
+    // n_om drives theta (I), p_C (Np) and theta_C (Nt): L Q_om L^T on rows/cols {6:9,18:21,21:24};
+    // the diagonal of the theta block was added above.
+    auto at = [&](int j) {
+      const d2 p = f2[(j >> 1) * PS];
+      return (j & 1) ? p.y : p.x;
+    };
+    double Lr[3][3];
+#pragma unroll
+    for (int v = 0; v < 3; ++v)
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        Lr[v][k] = (g == 2) ? ((k == v) ? 1.0 : 0.0) : (g == 6) ? at(FX3_NP + 3 * v + k) : at(FX3_NT + 3 * v + k);
+#pragma unroll
+    for (int cb = 0; cb < 3; ++cb) {
+      const int c0 = (cb == 0) ? 6 : (cb == 1) ? 18 : 21;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double Lc[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          Lc[k] = (cb == 0) ? ((k == j) ? 1.0 : 0.0) : (cb == 1) ? at(FX3_NP + 3 * j + k) : at(FX3_NT + 3 * j + k);
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) acc += Lr[v][k] * qd(3 + k) * Lc[k];
+          if (!(g == 2 && cb == 0)) X[c0 + j][v] += acc;
+        }
+      }
+    }
+  }
+}
+
+// ---- camera update on the register tile ------------------------------------------------------------------
+// "u3 record": per-filter exchange area of the eight lanes (doubles).  Element j of the record of filter
+// q (of QS filters interleaved pair-wise) lives at rec[((j >> 1) * QS) * 2 + (j & 1)], rec already offset
+// by 2 * q: the same pair of all QS filters of a warp is one contiguous 16 * QS bytes.
+constexpr int U3_S = 0;      // 7x7  S = H P H^T + R         (+1 pad)
+constexpr int U3_SINV = 50;  // 7x7  inv(S)                  (+1 pad)
+constexpr int U3_K = 100;    // 24x7 K
+constexpr int U3_WH = 268;   // 24x7 W(:, h_m),  W = (I - K H) P
+constexpr int U3_KR = 436;   // 24x7 K R
+constexpr int U3_SIZE = 604;
+
+template <int QS>
+ESKF_HD double& u3_at(double* rec, int j) {
+  return rec[((j >> 1) * QS) * 2 + (j & 1)];
+}
+template <int QS>
+ESKF_HD double u3_get(const double* rec, int j) {
+  return rec[((j >> 1) * QS) * 2 + (j & 1)];
+}
+// N consecutive record elements starting at element B (any parity), fetched as pairs
+template <int QS, int N>
+struct U3Row {
+  d2 p[(N + 2) / 2 + 1];
+  int b0;
+  ESKF_HD void load(const double* rec, int B) {
+    b0 = B & 1;
+    const d2* r2 = reinterpret_cast<const d2*>(rec);
+#pragma unroll
+    for (int j = 0; j < (N + 2) / 2; ++j)
+      if (2 * j < N + b0) p[j] = r2[((B >> 1) + j) * QS];
+  }
+  ESKF_HD double operator()(int i) const {
+    const int e = i + b0;
+    return (e & 1) ? p[e >> 1].y : p[e >> 1].x;
+  }
+};
+
+// owner of measurement row m: column h_m = ESKF_HSET(m) belongs to lane h_m / 3, tile column h_m % 3
+// U0a: lanes 5..7 publish their columns of S (Filter.py:355).
+template <int QS>
+ESKF_HD void upd3_publish_S(const double (&X)[24][3], int g, const double* rd, double* rec) {
+#pragma unroll
+  for (int m = 0; m < 7; ++m) {
+    const int h = ESKF_HSET(m);
+    if (g == h / 3) {
+#pragma unroll
+      for (int i = 0; i < 7; ++i) u3_at<QS>(rec, U3_S + 7 * i + m) = X[ESKF_HSET(i)][h % 3] + ((i == m) ? rd[m] : 0.0);
+    }
+  }
+}
+
+// U1: gain rows 3g..3g+2  K = (P H^T) inv(S)  (Filter.py:357), published together with K R; delta = K res
+// for the same rows.
+template <int QS>
+ESKF_HD void upd3_gain(const double (&X)[24][3], int g, double* rec, const double* res, const double* rd, double (&K)[3][7],
+                       double (&dl)[3]) {
+  double si[49];
+#pragma unroll
+  for (int j = 0; j < 49; ++j) si[j] = u3_get<QS>(rec, U3_SINV + j);
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    dl[v] = 0.0;
+#pragma unroll
+    for (int m = 0; m < 7; ++m) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) acc += X[ESKF_HSET(j)][v] * si[7 * j + m];  // P(r, h_j) = P(h_j, r)
+      K[v][m] = acc;
+      dl[v] += acc * res[m];
+      u3_at<QS>(rec, U3_K + 7 * (3 * g + v) + m) = acc;
+      u3_at<QS>(rec, U3_KR + 7 * (3 * g + v) + m) = acc * rd[m];
+    }
+  }
+}
+
+// U2a: X <- (I - K H) X  (Joseph factor, Filter.py:384), then lanes 5..7 publish the columns h_m of W.
+// The diagonal entries of I - K H are formed first, 1 - K[h_a][a], exactly as the reference's I - K @ H does:
+// with a prior >> R they are O(1e-12) and everything they multiply is cancellation dominated, so the order
+// of the roundings is kept (tests/test_conditioning.py).
+template <int QS>
+ESKF_HD void upd3_w_pass(double (&X)[24][3], int g, double* rec) {
+  // rows outside H first (they read the still untouched rows h_m) ...
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    if (i == 15 || i >= 18) continue;
+    U3Row<QS, 7> k;
+    k.load(rec, U3_K + 7 * i);
+#pragma unroll
+    for (int m = 0; m < 7; ++m)
+#pragma unroll
+      for (int v = 0; v < 3; ++v) X[i][v] -= k(m) * X[ESKF_HSET(m)][v];
+  }
+  // ... then the seven rows h_a themselves
+  double w[7][3];
+#pragma unroll
+  for (int a = 0; a < 7; ++a) {
+    const int i = ESKF_HSET(a);
+    U3Row<QS, 7> k;
+    k.load(rec, U3_K + 7 * i);
+    const double cd = 1.0 - k(a);
+#pragma unroll
+    for (int v = 0; v < 3; ++v) w[a][v] = cd * X[i][v];
+#pragma unroll
+    for (int m = 0; m < 7; ++m) {
+      if (m == a) continue;
+#pragma unroll
+      for (int v = 0; v < 3; ++v) w[a][v] -= k(m) * X[ESKF_HSET(m)][v];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 7; ++a)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) X[ESKF_HSET(a)][v] = w[a][v];
+#pragma unroll
+  for (int m = 0; m < 7; ++m) {
+    const int h = ESKF_HSET(m);
+    if (g == h / 3) {
+#pragma unroll
+      for (int i = 0; i < 24; ++i) u3_at<QS>(rec, U3_WH + 7 * i + m) = X[i][h % 3];
+    }
+  }
+}
+
+// U2b: X <- W (I - K H)^T for the tile columns j = 3g+v:  W(:,j) (1 - K[j][a]) - sum_{m != a} W(:,h_m) K[j][m]
+template <int QS>
+ESKF_HD void upd3_finish_a(double (&X)[24][3], int g, const double* rec) {
+  double Kz[3][7], cdv[3];
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    cdv[v] = 1.0;
+#pragma unroll
+    for (int m = 0; m < 7; ++m) {
+      const double k = u3_get<QS>(rec, U3_K + 7 * (3 * g + v) + m);
+      const bool diag = (ESKF_HSET(m) == 3 * g + v);
+      Kz[v][m] = diag ? 0.0 : k;
+      if (diag) cdv[v] = 1.0 - k;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    U3Row<QS, 7> wh;
+    wh.load(rec, U3_WH + 7 * i);
+#pragma unroll
+    for (int v = 0; v < 3; ++v) X[i][v] = cdv[v] * X[i][v];
+#pragma unroll
+    for (int m = 0; m < 7; ++m)
+#pragma unroll
+      for (int v = 0; v < 3; ++v) X[i][v] -= wh(m) * Kz[v][m];
+  }
+}
+
+// U2c: X += (K R) K(tile rows)^T  (Filter.py:384), then the reset P <- G P G^T with
+// G = I - [delta_theta / 2]x on 6:9 and 21:24 (Filter.py:386-390).
+template <int QS>
+ESKF_HD void upd3_finish_b(double (&X)[24][3], int g, const double* rec, const double* dth, const double* dthc) {
+  double K[3][7];
+#pragma unroll
+  for (int v = 0; v < 3; ++v)
+#pragma unroll
+    for (int m = 0; m < 7; ++m) K[v][m] = u3_get<QS>(rec, U3_K + 7 * (3 * g + v) + m);
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    U3Row<QS, 7> kr;
+    kr.load(rec, U3_KR + 7 * i);
+    double z[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int m = 0; m < 7; ++m)
+#pragma unroll
+      for (int v = 0; v < 3; ++v) z[v] += kr(m) * K[v][m];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) X[i][v] += z[v];
+  }
+  const double gt[3] = {0.5 * dth[0], 0.5 * dth[1], 0.5 * dth[2]};
+  const double gc[3] = {0.5 * dthc[0], 0.5 * dthc[1], 0.5 * dthc[2]};
+  // G P: rows 6:9 and 21:24 of every column;  (I - [g]x) = [[1, g2, -g1], [-g2, 1, g0], [g1, -g0, 1]]
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    const double a0 = X[6][v], a1 = X[7][v], a2 = X[8][v];
+    X[6][v] = a0 + gt[2] * a1 - gt[1] * a2;
+    X[7][v] = -gt[2] * a0 + a1 + gt[0] * a2;
+    X[8][v] = gt[1] * a0 - gt[0] * a1 + a2;
+    const double b0 = X[21][v], b1 = X[22][v], b2 = X[23][v];
+    X[21][v] = b0 + gc[2] * b1 - gc[1] * b2;
+    X[22][v] = -gc[2] * b0 + b1 + gc[0] * b2;
+    X[23][v] = gc[1] * b0 - gc[0] * b1 + b2;
+  }
+  // (.) G^T: the three columns of lane 2 (6:9) and lane 7 (21:24)
+  if (g == 2 || g == 7) {
+    const double h0 = (g == 2) ? gt[0] : gc[0], h1 = (g == 2) ? gt[1] : gc[1], h2 = (g == 2) ? gt[2] : gc[2];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+      const double a0 = X[i][0], a1 = X[i][1], a2 = X[i][2];
+      X[i][0] = a0 + h2 * a1 - h1 * a2;
+      X[i][1] = -h2 * a0 + a1 + h0 * a2;
+      X[i][2] = h1 * a0 - h0 * a1 + a2;
+    }
+  }
+}
+
+}  // namespace eskf

@@ -254,8 +254,8 @@ __global__ void __launch_bounds__(32 + 8 * F, 1) eskf_kernel(const __grid_consta
             acc[i] = oap[kk * 6 + 3 + i];
           }
           if (noisy) {
-            double z[6];
-            normal6(a.seed, (uint64_t)gid, (uint64_t)kk, RNG_KIND_IMU, z);
+            double z[8];
+            normal8(a.seed, (uint64_t)gid, (uint64_t)kk, RNG_KIND_IMU, z);
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
               om[i] += a.imu_noise[i] * z[i];
@@ -305,8 +305,7 @@ __global__ void __launch_bounds__(32 + 8 * F, 1) eskf_kernel(const __grid_consta
           double notch = a.notch[mrow];
           if (noisy) {
             double z[8];
-            normal6(a.seed, (uint64_t)gid, (uint64_t)e, RNG_KIND_CAM, z);
-            normal2(a.seed, (uint64_t)gid, (uint64_t)e, RNG_KIND_CAM2, z + 6);
+            normal8(a.seed, (uint64_t)gid, (uint64_t)e, RNG_KIND_CAM, z);
             double dth[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -348,7 +347,7 @@ __global__ void __launch_bounds__(32 + 8 * F, 1) eskf_kernel(const __grid_consta
 #pragma unroll
           for (int i = 0; i < 24; ++i) d[i] = up[UP_DELTA + i];
           inject_error(a.model, s, d);
-          probe_eval(a.model, s.dofs, s.notch, pk, ptr);
+          probe_update(a.model, s.dofs, s.notch, pk, ptr);
           after_update = true;
           n_upd += 1.0;
         } else {

@@ -1,0 +1,819 @@
+// eskf_kernel3: the warp-specialised persistent VI-ESKF kernel for sm_100a, covariance resident in
+// registers for the propagation AND the camera update.
+//
+// One CTA owns F filters for a whole launch (a whole trajectory in eskf_run).  Warps are roles:
+//   warp 0  IMU     lane = filter: p, v, q of the nominal state (Filter._predict_nominal, Filter.py:232-247,
+//                   equations.py:72-86) and R_WB_old (Filter.py:227)
+//   warp 1  CAMERA  lane = filter: p_cam, q_cam (equations.py:88-98), the measurement residual
+//                   (Filter.py:363-375), status word
+//   warp 3  JACOB   lane = filter: dofs, notch chain, probe forward kinematics (Probe.py:470-480) and the
+//                   Jacobian blocks of Fx / Fi (Filter._predict_error, Filter.py:249-342)
+//   warp 2  STAGER  lane = filter: stages the IMU sample stream (dt, om, acc) into a 4-slot shared-memory
+//                   ring two steps ahead and adds the Monte-Carlo noise (Philox4x32-10 + single-precision
+//                   Box-Muller on the SFU); stages the camera measurement of the epoch
+//                   (Imu.eval_expr_single / Filter.propagate_imu, Imu.py:141-196, Filter.py:187-217;
+//                   VisualTraj.at_index, VisualTrajectory.py:120-134)
+//   warps 4.. COVARIANCE  eight lanes per filter, lane g keeps columns 3g..3g+2 of the 24x24 covariance in
+//                   REGISTERS (72 doubles) for the whole launch -- see eskf_cov3.cuh for the algebra:
+//                   one propagation = two local sparse products around ONE transposition through shared
+//                   memory (72 STS.64 + 36 LDS.128 per lane); the camera update (gain, Joseph form,
+//                   reset) works on the same register tile and exchanges only S, K, K R, W(:,h) (7-wide
+//                   records) between the eight lanes of a filter, with warp-level synchronisation.
+// The scalar roles of step k run concurrently with the covariance role of step k-1; all roles meet at one
+// CTA barrier per step.  Records exchanged through shared memory are double buffered:
+//   RING[4]  samples (slot (k+1)&3 = new sample of step k, slot k&3 = old sample)       STAGER -> IMU, CAMERA, JACOB
+//   RO/RW/V[2] R_WB_old, R_WB and v at the start of step k (slot k&1)                   IMU -> CAMERA, JACOB
+//   PK[2]    probe kinematics + notch, notch' at the start of step k (slot k&1)         JACOB -> CAMERA
+//   FXB[2]   Jacobian blocks of the step (fx3 layout, [pair][filter] so that the writer's STS.128 and the
+//            readers' broadcast LDS.128 are both conflict free)                         JACOB -> COVARIANCE
+// Register budget by role (setmaxnreg): scalar warps shrink to REG_S, covariance warps grow to REG_C
+// (eskf_launch3.cu).
+#pragma once
+#include "eskf_cov3.cuh"
+#include "eskf_kernel.cuh"
+
+// profiling experiment switches (python -m dvi_ekf_b200.build --exp=...): time one side of the kernel alone
+#ifdef ESKF_EXP_NO_SCALAR
+#define ESKF3_SCALAR_ON(it) ((it) < 2)  // scalar roles only fill both record slots once per epoch
+#else
+#define ESKF3_SCALAR_ON(it) true
+#endif
+#ifdef ESKF_EXP_NO_COV
+#define ESKF3_COV_ON false
+#else
+#define ESKF3_COV_ON true
+#endif
+
+namespace eskf {
+
+constexpr int RS3 = 26;          // row stride of the transposition buffer: even (16-byte rows) and
+constexpr int TB3_STRIDE = 632;  // 24*26 + 8; = 8 (mod 16) doubles => conflict-free STS.64 / LDS.128
+
+// scalar exchange block, element-major: element j of filter f at SX[j * F + f]
+constexpr int SX3_RING = 0;     // 4 x 8: om(3) acc(3) dt pad
+constexpr int SX3_RO = 32;      // 2 x 9
+constexpr int SX3_RW = 50;      // 2 x 9
+constexpr int SX3_V = 68;       // 2 x 3
+constexpr int SX3_PK = 74;      // 2 x 17: p(3) R(9) z6(3) notch notch'
+constexpr int SX3_MEAS = 108;   // 8: cam pos(3) quat(4) notch
+constexpr int SX3_RES = 116;    // 7: measurement residual            CAMERA -> COVARIANCE
+constexpr int SX3_OK = 123;     // residual valid
+constexpr int SX3_DELTA = 124;  // 24: error state K res              COVARIANCE -> scalar roles
+constexpr int SX3_OK2 = 148;    // update applied
+constexpr int SX3_QD = 149;     // 13: diag(Q)
+constexpr int SX3_RD = 162;     // 7: diag(R)
+constexpr int SX3_ST = 169;     // 12: statistics partials (epilogue)
+constexpr int SX3_TR = 182;     // 24: trigonometry cache of the probe kinematics (private to JACOB)
+constexpr int SX3_SIZE = 206;
+
+template <int F>
+struct Lay3 {
+  static constexpr int TB = 0;                  // [F][TB3_STRIDE]  (u3 records of a warp's four filters during the update)
+  static constexpr int SX = F * TB3_STRIDE;     // [SX3_SIZE][F]
+  static constexpr int FXB = SX + SX3_SIZE * F; // [2][FX3_NPAIR][F] d2
+  static constexpr int TOTAL = FXB + 2 * FX3_NPAIR * 2 * F;  // doubles
+  static_assert((SX % 2) == 0 && (FXB % 2) == 0, "16-byte alignment");
+  static_assert(4 * U3_SIZE <= 4 * TB3_STRIDE, "update records must fit the transposition buffers of a warp");
+};
+
+template <int N>
+__device__ __forceinline__ void reg_inc3() {
+  if constexpr (N > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dec3() {
+  if constexpr (N > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(N));
+}
+
+struct Ctx3 {
+  double* smem;
+  int64_t f0;      // first local filter of the CTA
+  int nf;          // filters of this CTA that exist
+  int64_t gid0;    // global id of the CTA's first filter
+  int64_t traj;
+  const int32_t* n_prop;
+  const double* dtp;
+};
+
+// ---------------------------------------------------------------------------------------------
+// cooperative, coalesced tile store (all threads of the CTA)
+template <int F, int NTHR>
+__device__ __forceinline__ void store_tiles3(const KArgs& a, const Ctx3& c, int tid) {
+  const double* sT = c.smem + Lay3<F>::TB;
+  for (int idx = tid; idx < c.nf * 576; idx += NTHR) {
+    const int f = idx / 576, r = idx - f * 576;
+    const int i = r / 24, j = r - i * 24;
+    a.P[(c.f0 + f) * 576 + r] = sT[f * TB3_STRIDE + i * RS3 + j];
+  }
+}
+
+// statistics rows (Filter.calculate_dof_metric / update_mse) assembled by warp 0 from the partials the
+// scalar roles left in SX3_ST: [0] mseA_last [1] mseA_sum [2] mseB_last [3] mseB_sum [4] n_upd [5] status
+// [6..11] (dofs - gt)^2
+template <int F>
+__device__ __forceinline__ void write_stats3(const KArgs& a, const Ctx3& c, int lane) {
+  if (!(a.stats_out || a.stats_sum)) return;
+  const double* st = c.smem + Lay3<F>::SX + SX3_ST * F + lane;
+  double row[ESKF_NSTAT];
+#pragma unroll
+  for (int i = 0; i < ESKF_NSTAT; ++i) row[i] = 0.0;
+  if (lane < c.nf) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      row[i] = st[(6 + i) * F];
+      acc += row[i];
+    }
+    row[6] = acc / 6.0;
+    row[7] = (st[0] + st[2 * F]) / 12.0;
+    row[8] = (st[F] + st[3 * F]) / 12.0;
+    row[9] = st[4 * F];
+    row[10] = st[5 * F];
+    row[11] = 1.0;
+    if (a.stats_out) {
+#pragma unroll
+      for (int i = 0; i < ESKF_NSTAT; ++i) a.stats_out[(c.f0 + lane) * ESKF_NSTAT + i] = row[i];
+    }
+  }
+  if (a.stats_sum) {
+#pragma unroll
+    for (int i = 0; i < ESKF_NSTAT; ++i) {
+      double v = row[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) atomicAdd(a.stats_sum + i, v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// role 0: IMU nominal state
+template <int F, int NTHR>
+__device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lane) {
+  using L = Lay3<F>;
+  const bool act = lane < c.nf;
+  double* sx = c.smem + L::SX + lane;
+  d2* fxb = reinterpret_cast<d2*>(c.smem + L::FXB) + lane;  // pair j2 of slot s at fxb[(s * FX3_NPAIR + j2) * F]
+  double p[3], v[3], q[4], Rwb[9], Rold[9];
+  double mse_last = 0.0, mse_sum = 0.0;
+  if (act) {
+    const double* xg = a.x + (c.f0 + lane) * NX;
+    const double* rg = a.Ro + (c.f0 + lane) * 9;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      p[i] = xg[i];
+      v[i] = xg[3 + i];
+      sx[(SX3_V + i) * F] = v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = xg[6 + i];
+    quat_to_rot(q, Rwb);  // R_WB of the first step is rot(q); R_WB_old may be stale (quirk Q8)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      Rold[i] = rg[i];
+      sx[(SX3_RO + i) * F] = Rold[i];
+      sx[(SX3_RW + i) * F] = Rwb[i];
+    }
+  }
+  __syncthreads();  // prologue
+  int64_t k = 0;
+  for (int64_t e = 0; e < a.E; ++e) {
+    const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
+    for (int it = 0; it <= n; ++it) {
+      if (act && it < n && ESKF3_SCALAR_ON(it)) {
+        const int64_t kk = k + it;
+        const double* uo = sx + (SX3_RING + 8 * (int)(kk & 3)) * F;
+        const double* un = sx + (SX3_RING + 8 * (int)((kk + 1) & 3)) * F;
+        double om_old[3], acc_old[3], om[3], acc[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          om_old[i] = uo[i * F];
+          acc_old[i] = uo[(3 + i) * F];
+          om[i] = un[i * F];
+          acc[i] = un[(3 + i) * F];
+        }
+        const double dt = un[6 * F];
+        {  // rows 3:9 of Fx (Filter.py:253-255) from the buffered R_WB_old / om_old / acc_old: this role has them
+          double fx[FX3_SIZE];
+          jac_rows_ab(Rold, dt, om_old, acc_old, fx);
+          d2* dst = fxb + ((it & 1) * FX3_NPAIR) * F;
+#pragma unroll
+          for (int j = FX3_AB / 2; j < FX3_MAIN / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
+        }
+        imu_nominal_step(p, v, q, Rwb, dt, om_old, acc_old, om, acc, Rold);
+        const int s = (int)((kk + 1) & 1);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          Rwb[i] = Rold[i];
+          sx[(SX3_RO + 9 * s + i) * F] = Rold[i];
+          sx[(SX3_RW + 9 * s + i) * F] = Rold[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) sx[(SX3_V + 3 * s + i) * F] = v[i];
+      }
+      __syncthreads();
+    }
+    k += n;
+    if (!a.do_update) continue;
+    __syncthreads();  // U0 | U1
+    __syncthreads();  // U1 | U2
+    if (act) {
+      if (sx[SX3_OK2 * F] != 0.0) {  // state (+) error state, IMU part (state.py:46-53,116-121)
+        const double th[3] = {sx[(SX3_DELTA + 6) * F], sx[(SX3_DELTA + 7) * F], sx[(SX3_DELTA + 8) * F]};
+        double dq[4], qn[4];
+        quat_about_axis(sqrt(th[0] * th[0] + th[1] * th[1] + th[2] * th[2]), th, dq);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          p[i] += sx[(SX3_DELTA + i) * F];
+          v[i] += sx[(SX3_DELTA + 3 + i) * F];
+        }
+        quat_mul(q, dq, qn);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q[i] = qn[i];
+        quat_to_rot(q, Rwb);  // R_WB of the next step; R_WB_old keeps the pre-update value (quirk Q8)
+        const int s = (int)(k & 1);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sx[(SX3_RW + 9 * s + i) * F] = Rwb[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) sx[(SX3_V + 3 * s + i) * F] = v[i];
+      }
+      if (a.cam_ref && a.imu_ref) {  // IMU half of Filter.calculate_update_mse (Filter.py:408-413)
+        const double* ir = a.imu_ref + (c.traj * a.E + e) * 6;
+        double ei[3], acc2 = 0.0;
+        euler_xyz_deg(q, ei);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const double d2_ = v[i] - ir[i], d3 = ei[i] - ir[3 + i];
+          acc2 += d2_ * d2_ + d3 * d3;
+        }
+        mse_last = acc2;
+        mse_sum += acc2;
+      }
+    }
+    __syncthreads();  // U2 done
+  }
+  // ---- write back ----
+  if (act) {
+    double* xg = a.x + (c.f0 + lane) * NX;
+    double* ug = a.u + (c.f0 + lane) * 6;
+    double* rg = a.Ro + (c.f0 + lane) * 9;
+    const double* uo = sx + (SX3_RING + 8 * (int)(k & 3)) * F;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      xg[i] = p[i];
+      xg[3 + i] = v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xg[6 + i] = q[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) ug[i] = uo[i * F];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) rg[i] = Rold[i];
+    sx[(SX3_ST + 0) * F] = mse_last;
+    sx[(SX3_ST + 1) * F] = mse_sum;
+  }
+  __syncthreads();  // tiles dumped, statistics partials written
+  store_tiles3<F, NTHR>(a, c, threadIdx.x);
+  write_stats3<F>(a, c, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// role 1: camera nominal state + measurement residual
+template <int F, int NTHR>
+__device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lane) {
+  using L = Lay3<F>;
+  const bool act = lane < c.nf;
+  double* sx = c.smem + L::SX + lane;
+  double pc[3], qc[4];
+  double mse_last = 0.0, mse_sum = 0.0, n_upd = 0.0;
+  int32_t st = 0;
+  if (act) {
+    const double* xg = a.x + (c.f0 + lane) * NX;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) pc[i] = xg[19 + i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qc[i] = xg[22 + i];
+    st = a.status[c.f0 + lane];
+  }
+  __syncthreads();  // prologue
+  int64_t k = 0;
+  for (int64_t e = 0; e < a.E; ++e) {
+    const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
+    for (int it = 0; it <= n; ++it) {
+      if (act && it < n && ESKF3_SCALAR_ON(it)) {
+        const int64_t kk = k + it;
+        const double* uo = sx + (SX3_RING + 8 * (int)(kk & 3)) * F;
+        const double* un = sx + (SX3_RING + 8 * (int)((kk + 1) & 3)) * F;
+        const int s = (int)(kk & 1);
+        double om_old[3], om[3], vpre[3], Rwb[9], pkp[3], pkR[9], pkz[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          om_old[i] = uo[i * F];
+          om[i] = un[i * F];
+          vpre[i] = sx[(SX3_V + 3 * s + i) * F];
+          pkp[i] = sx[(SX3_PK + 17 * s + i) * F];
+          pkz[i] = sx[(SX3_PK + 17 * s + 12 + i) * F];
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          Rwb[i] = sx[(SX3_RW + 9 * s + i) * F];
+          pkR[i] = sx[(SX3_PK + 17 * s + 3 + i) * F];
+        }
+        const double dt = un[6 * F];
+        const double notch_d = sx[(SX3_PK + 17 * s + 16) * F];
+        cam_nominal_step(pc, qc, vpre, Rwb, dt, om_old, om, pkp, pkR, pkz, notch_d);
+      }
+      __syncthreads();
+    }
+    k += n;
+    if (!a.do_update) continue;
+    // ---- U0: residual (Filter.py:363-375) ----
+    if (lane < F) {
+      bool ok = false;
+      if (act) {
+        double cam[7], res[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) cam[i] = sx[(SX3_MEAS + i) * F];
+        const double notch_meas = sx[(SX3_MEAS + 7) * F];
+        const double notch0 = sx[(SX3_PK + 17 * (int)(k & 1) + 15) * F];
+        Nominal s;  // only pc, qc, notch[0] are read by update_residual
+#pragma unroll
+        for (int i = 0; i < 3; ++i) s.pc[i] = pc[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s.qc[i] = qc[i];
+        s.notch[0] = notch0;
+        ok = update_residual(s, cam, cam + 3, notch_meas, res);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) sx[(SX3_RES + i) * F] = res[i];
+        if (!ok) st |= ESKF_STATUS_ASIN_DOMAIN;
+      }
+      sx[SX3_OK * F] = ok ? 1.0 : 0.0;
+    }
+    __syncthreads();  // U0 | U1
+    __syncthreads();  // U1 | U2
+    if (act) {
+      if (sx[SX3_OK2 * F] != 0.0) {  // camera part of the injection, incl. the dqc axis slip (quirk Q4, state.py:124)
+        const double th[3] = {sx[(SX3_DELTA + 6) * F], sx[(SX3_DELTA + 7) * F], sx[(SX3_DELTA + 8) * F]};
+        const double thc[3] = {sx[(SX3_DELTA + 21) * F], sx[(SX3_DELTA + 22) * F], sx[(SX3_DELTA + 23) * F]};
+        double dqc[4], qn[4];
+        quat_about_axis(sqrt(thc[0] * thc[0] + thc[1] * thc[1] + thc[2] * thc[2]), th, dqc);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) pc[i] += sx[(SX3_DELTA + 18 + i) * F];
+        quat_mul(qc, dqc, qn);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qc[i] = qn[i];
+        n_upd += 1.0;
+      } else {
+        st |= ESKF_STATUS_UPDATE_SKIPPED;
+      }
+      if (a.cam_ref && a.imu_ref) {  // camera half of Filter.calculate_update_mse (Filter.py:401-406)
+        const double* cr = a.cam_ref + (c.traj * a.E + e) * 6;
+        double ec[3], acc2 = 0.0;
+        euler_xyz_deg(qc, ec);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const double d0 = cr[i] - pc[i], d1 = cr[3 + i] - ec[i];
+          acc2 += d0 * d0 + d1 * d1;
+        }
+        mse_last = acc2;
+        mse_sum += acc2;
+      }
+    }
+    __syncthreads();  // U2 done
+  }
+  if (act) {
+    double* xg = a.x + (c.f0 + lane) * NX;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) xg[19 + i] = pc[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xg[22 + i] = qc[i];
+    a.status[c.f0 + lane] = st;
+    sx[(SX3_ST + 2) * F] = mse_last;
+    sx[(SX3_ST + 3) * F] = mse_sum;
+    sx[(SX3_ST + 4) * F] = n_upd;
+    sx[(SX3_ST + 5) * F] = (double)st;
+  }
+  __syncthreads();
+  store_tiles3<F, NTHR>(a, c, threadIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// role 2: dofs / notch, probe kinematics, Jacobian blocks (rows 18:24; rows 3:9 come from the IMU role).
+// The probe kinematics and their trigonometry cache live in shared memory (PK slots, TR), not in registers.
+template <int F, int NTHR>
+__device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lane) {
+  using L = Lay3<F>;
+  const bool act = lane < c.nf;
+  double* sx = c.smem + L::SX + lane;
+  d2* fxb = reinterpret_cast<d2*>(c.smem + L::FXB) + lane;  // pair j2 of slot s at fxb[(s * FX3_NPAIR + j2) * F]
+  const TRView<F> trv{sx + SX3_TR * F};
+  auto pkv = [&](int s) { return PKView<F>{sx + (SX3_PK + 17 * s) * F}; };
+  auto put_notch = [&](int s, const double* notch) {
+    sx[(SX3_PK + 17 * s + 15) * F] = notch[0];
+    sx[(SX3_PK + 17 * s + 16) * F] = notch[1];
+  };
+  double dofs[6], notch[3], sig_om[3] = {0, 0, 0};
+  bool imu_q = false;
+  if (act) {
+    const double* xg = a.x + (c.f0 + lane) * NX;
+    const double* pg = a.par + (c.f0 + lane) * PAR_STRIDE;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dofs[i] = xg[10 + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      notch[i] = xg[16 + i];
+      sig_om[i] = pg[PAR_SIGOM + i];
+    }
+    imu_q = (pg[PAR_QD + 3] != 0.0) || (pg[PAR_QD + 4] != 0.0) || (pg[PAR_QD + 5] != 0.0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) trv.ang(j) = __longlong_as_double(0x7ff8000000000000LL);  // nothing cached yet
+    probe_update_v(a.model, dofs, notch, pkv(0), trv);
+    put_notch(0, notch);
+  }
+  __syncthreads();  // prologue
+  int64_t k = 0;
+  for (int64_t e = 0; e < a.E; ++e) {
+    const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
+    for (int it = 0; it <= n; ++it) {
+      if (act && it < n && ESKF3_SCALAR_ON(it)) {
+        const int64_t kk = k + it;
+        const double* uo = sx + (SX3_RING + 8 * (int)(kk & 3)) * F;
+        const double dt = sx[(SX3_RING + 8 * (int)((kk + 1) & 3) + 6) * F];
+        const int s = (int)(kk & 1), sn = s ^ 1;
+        // post-predict (dofs, notch) and their probe kinematics -> PK slot of the next step
+        const PKView<F> pk = pkv(sn);
+        if (dofs_notch_step(a.model, dofs, notch, dt)) {
+          probe_update_v(a.model, dofs, notch, pk, trv);
+        } else {
+          const PKView<F> po = pkv(s);
+#pragma unroll
+          for (int i = 0; i < PK_SIZE; ++i) pk.b[i * F] = po.b[i * F];
+        }
+        put_notch(sn, notch);
+        double om_old[3], Ro[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) om_old[i] = uo[i * F];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Ro[i] = sx[(SX3_RO + 9 * s + i) * F];
+        d2* dst = fxb + ((it & 1) * FX3_NPAIR) * F;
+        double fx[FX3_SIZE];
+        // every row group is shipped as soon as it is final (short register live ranges)
+        jac_rows_h2(a.model, notch[1], pk, trv, dt, om_old, sig_om, fx);
+#pragma unroll
+        for (int j = 0; j < FX3_H1 / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
+        jac_rows_h1(a.model, dofs, pk, trv, Ro, dt, om_old, sig_om, fx);
+#pragma unroll
+        for (int j = FX3_H1 / 2; j < FX3_AB / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
+        if (imu_q) {
+          jac_rows_noise(pk, Ro, dt, fx);
+#pragma unroll
+          for (int j = FX3_NPAIR_MAIN; j < FX3_NPAIR; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
+        }
+      }
+      __syncthreads();
+    }
+    k += n;
+    if (!a.do_update) continue;
+    __syncthreads();  // U0 | U1
+    __syncthreads();  // U1 | U2
+    if (act) {
+      if (sx[SX3_OK2 * F] != 0.0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+          if (!((a.model.frozen_mask >> i) & 1)) dofs[i] += sx[(SX3_DELTA + 9 + i) * F];  // Filter.py:377-379
+#pragma unroll
+        for (int i = 0; i < 3; ++i) notch[i] += sx[(SX3_DELTA + 15 + i) * F];
+        probe_update_v(a.model, dofs, notch, pkv((int)(k & 1)), trv);
+        put_notch((int)(k & 1), notch);
+      }
+    }
+    __syncthreads();  // U2 done
+  }
+  if (act) {
+    double* xg = a.x + (c.f0 + lane) * NX;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xg[10 + i] = dofs[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) xg[16 + i] = notch[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const double d = dofs[i] - a.gt_dofs[i];
+      sx[(SX3_ST + 6 + i) * F] = d * d;
+    }
+  }
+  __syncthreads();
+  store_tiles3<F, NTHR>(a, c, threadIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// role 3: sample-stream stager + Monte-Carlo noise
+template <int F, int NTHR>
+__device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int lane) {
+  using L = Lay3<F>;
+  const bool act = lane < c.nf;
+  double* sx = c.smem + L::SX + lane;
+  const int64_t gid = c.gid0 + lane;
+  const bool noisy = a.noise_on && !(a.noise_free0 && gid == 0);
+  const double* oap =
+      a.om_acc ? (a.stream_per_filter ? a.om_acc + (c.f0 + lane) * a.T * 6 : a.om_acc + c.traj * a.T * 6) : nullptr;
+  auto stage_sample = [&](int64_t j) {  // sample of step j -> ring slot (j + 1) & 3
+    double* dst = sx + (SX3_RING + 8 * (int)((j + 1) & 3)) * F;
+    double u[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) u[i] = oap[j * 6 + i];
+    if (noisy) {
+      double z[8];
+      normal8(a.seed, (uint64_t)gid, (uint64_t)j, RNG_KIND_IMU, z);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) u[i] += a.imu_noise[i] * z[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dst[i * F] = u[i];
+    dst[6 * F] = c.dtp[j];
+  };
+  auto stage_meas = [&](int64_t e) {
+    const int64_t mrow = a.meas_per_filter ? (c.f0 + lane) : (c.traj * a.E + e);
+    double cam[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) cam[i] = a.cam[mrow * 7 + i];
+    double notch = a.notch[mrow];
+    if (noisy) {
+      double z[8];
+      normal8(a.seed, (uint64_t)gid, (uint64_t)e, RNG_KIND_CAM, z);
+      double dth[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        cam[i] += a.cam_noise[i] * z[i];
+        dth[i] = a.cam_noise[3 + i] * z[3 + i];
+      }
+      // orientation noise: small body rotation of the measured quaternion (its norm is kept)
+      double dq[4], qn[4];
+      quat_about_axis(sqrt(dth[0] * dth[0] + dth[1] * dth[1] + dth[2] * dth[2]), dth, dq);
+      const double nq = sqrt(cam[3] * cam[3] + cam[4] * cam[4] + cam[5] * cam[5] + cam[6] * cam[6]);
+      quat_mul(cam + 3, dq, qn);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cam[3 + i] = qn[i] * nq;
+      notch += a.cam_noise[6] * z[6];
+    }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) sx[(SX3_MEAS + i) * F] = cam[i];
+    sx[(SX3_MEAS + 7) * F] = notch;
+  };
+  if (act) {
+    const double* ug = a.u + (c.f0 + lane) * 6;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sx[(SX3_RING + i) * F] = ug[i];  // slot 0: the buffered previous sample
+    sx[(SX3_RING + 6) * F] = 0.0;
+    if (a.T > 0 && oap) stage_sample(0);
+  }
+  __syncthreads();  // prologue
+  int64_t k = 0;
+  for (int64_t e = 0; e < a.E; ++e) {
+    const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
+    for (int it = 0; it <= n; ++it) {
+      if (act) {
+        if (it == 0 && a.do_update) stage_meas(e);
+        if (it < n && k + it + 1 < a.T && ESKF3_SCALAR_ON(it)) stage_sample(k + it + 1);
+      }
+      __syncthreads();
+    }
+    k += n;
+    if (!a.do_update) continue;
+    __syncthreads();  // U0 | U1
+    __syncthreads();  // U1 | U2
+    __syncthreads();  // U2 done
+  }
+  __syncthreads();
+  store_tiles3<F, NTHR>(a, c, threadIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// covariance role
+
+// inv(S) by the eight lanes of a filter: lane c < 7 owns column c of [S | I].  LU with partial pivoting
+// + back substitution, the same operations in the same order as eskf::inv7 (the host-checkable
+// restatement of np.linalg.inv -> LAPACK gesv, Filter.py:357); multipliers and U entries travel by
+// width-8 shuffles.  Reads S from / writes inv(S) to the u3 record.  False for an exactly singular or
+// non-finite S (the reference's LinAlgError branch, Filter.py:358-361).
+template <int QS>
+__device__ __forceinline__ bool inv7_group3(double* rec, int g) {
+  const unsigned FULL = 0xffffffffu;
+  const int c = (g < 7) ? g : 6;
+  double a[7], b[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    a[i] = u3_get<QS>(rec, U3_S + 7 * i + c);
+    b[i] = (i == c) ? 1.0 : 0.0;
+  }
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    int piv = k;
+    double best = fabs(a[k]);
+#pragma unroll
+    for (int i = k + 1; i < 7; ++i) {
+      const double v = fabs(a[i]);
+      if (v > best) {
+        best = v;
+        piv = i;
+      }
+    }
+    piv = __shfl_sync(FULL, piv, k, 8);
+    best = __shfl_sync(FULL, best, k, 8);
+    ok = ok && (best != 0.0);
+#pragma unroll
+    for (int i = k + 1; i < 7; ++i) {
+      if (piv == i) {
+        double t = a[k];
+        a[k] = a[i];
+        a[i] = t;
+        t = b[k];
+        b[k] = b[i];
+        b[i] = t;
+      }
+    }
+    const double rp = 1.0 / a[k];
+#pragma unroll
+    for (int i = k + 1; i < 7; ++i) {
+      const double l = __shfl_sync(FULL, a[i] * rp, k, 8);
+      a[i] -= l * a[k];
+      b[i] -= l * b[k];
+    }
+  }
+#pragma unroll
+  for (int i = 6; i >= 0; --i) {
+    double v = b[i];
+#pragma unroll
+    for (int k = i + 1; k < 7; ++k) {
+      const double uik = __shfl_sync(FULL, a[i], k, 8);
+      v -= uik * b[k];
+    }
+    const double uii = __shfl_sync(FULL, a[i], i, 8);
+    b[i] = v * (1.0 / uii);
+  }
+  double chk = 0.0;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) chk += b[i] * 0.0;  // NaN / inf detector
+  ok = ok && (chk == 0.0);
+  if (g < 7) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) u3_at<QS>(rec, U3_SINV + 7 * i + c) = b[i];
+  }
+  const unsigned bal = __ballot_sync(FULL, ok);
+  const unsigned lane = threadIdx.x & 31u;
+  return ((bal >> (lane & 24u)) & 0xffu) == 0xffu;
+}
+
+template <int F, int NTHR>
+__device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct) {
+  using L = Lay3<F>;
+  const int cf = ct >> 3;  // filter of this lane (padded filters run on an identity tile, never stored)
+  const int cg = ct & 7;   // state group owned
+  const unsigned gmask = 0xffu << (threadIdx.x & 24);
+  double* Tb = c.smem + L::TB + cf * TB3_STRIDE;
+  // u3 record of this filter: the transposition buffers of the warp's four filters, pair-interleaved
+  double* rec = c.smem + L::TB + (cf & ~3) * TB3_STRIDE + 2 * (cf & 3);
+  const double* sxc = c.smem + L::SX + cf;
+  double* sxw = c.smem + L::SX + cf;
+  const d2* fxb = reinterpret_cast<const d2*>(c.smem + L::FXB) + cf;
+  auto qd = [&](int j) { return sxc[(SX3_QD + j) * F]; };
+  const bool imu_q = (qd(3) != 0.0) || (qd(4) != 0.0) || (qd(5) != 0.0);
+  double qdv[3];  // diagonal process noise of this lane's three rows
+  fx3_noise_diag(cg, qd, qdv);
+
+  // X[i][v] = P[3g+v][i]: rows 3g..3g+2 of P, used as its columns 3g..3g+2 (a covariance is symmetric;
+  // the engine never relies on more than that)
+  double X[24][3];
+  auto dump_rows = [&]() {  // tile -> rows 3g..3g+2 of the buffer (16-byte stores)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      d2* row = reinterpret_cast<d2*>(Tb + (3 * cg + v) * RS3);
+#pragma unroll
+      for (int j = 0; j < 12; ++j) row[j] = d2{X[2 * j][v], X[2 * j + 1][v]};
+    }
+  };
+  auto load_rows = [&]() {
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      const d2* row = reinterpret_cast<const d2*>(Tb + (3 * cg + v) * RS3);
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        const d2 t = row[j];
+        X[2 * j][v] = t.x;
+        X[2 * j + 1][v] = t.y;
+      }
+    }
+  };
+
+  load_rows();
+  __syncthreads();  // prologue
+
+  for (int64_t e = 0; e < a.E; ++e) {
+    const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
+    for (int it = 0; it <= n; ++it) {
+      if (it >= 1 && ESKF3_COV_ON) {
+        const d2* f2 = fxb + (((it - 1) & 1) * FX3_NPAIR) * F;
+        // pass 1: T(:, 3g..3g+2) = Fx P(:, 3g..3g+2), rows stored as they are finished
+        fx3_apply_store<F, RS3>(X, f2, Tb + 3 * cg);
+        __syncwarp(gmask);
+        load_rows();  // X[k][v] = T(3g+v, k)
+        __syncwarp(gmask);
+        // pass 2: P'(3g+v, :) = Fx T(3g+v, :)^T
+        fx3_apply_inplace<F>(X, f2);
+        fx3_process_noise<F>(X, cg, f2, qdv, qd, imu_q);
+      }
+      __syncthreads();
+    }
+    if (!a.do_update) continue;
+    // ---- U0: S and its inverse (the scalar CAMERA role computes the residual meanwhile) ----
+    double rd[7];
+#pragma unroll
+    for (int m = 0; m < 7; ++m) rd[m] = sxc[(SX3_RD + m) * F];
+    upd3_publish_S<4>(X, cg, rd, rec);
+    __syncwarp(gmask);
+    const bool inv_ok = inv7_group3<4>(rec, cg);
+    __syncthreads();  // U0 | U1
+    const bool upd_c = inv_ok && (sxc[SX3_OK * F] != 0.0);
+    if (upd_c) {
+      double K[3][7], res[7], dl[3];
+#pragma unroll
+      for (int m = 0; m < 7; ++m) res[m] = sxc[(SX3_RES + m) * F];
+      upd3_gain<4>(X, cg, rec, res, rd, K, dl);
+#pragma unroll
+      for (int v = 0; v < 3; ++v) sxw[(SX3_DELTA + 3 * cg + v) * F] = dl[v];
+      if (a.K_out && cf < c.nf) {
+#pragma unroll
+        for (int v = 0; v < 3; ++v)
+#pragma unroll
+          for (int m = 0; m < 7; ++m) a.K_out[((c.f0 + cf) * 24 + 3 * cg + v) * 7 + m] = K[v][m];
+      }
+    }
+    if (cg == 0) sxw[SX3_OK2 * F] = upd_c ? 1.0 : 0.0;
+    __syncthreads();  // U1 | U2  (also orders the K / K R records of the eight lanes)
+    if (upd_c) {
+      upd3_w_pass<4>(X, cg, rec);
+      __syncwarp(gmask);
+      upd3_finish_a<4>(X, cg, rec);
+      const double dth[3] = {sxc[(SX3_DELTA + 6) * F], sxc[(SX3_DELTA + 7) * F], sxc[(SX3_DELTA + 8) * F]};
+      const double dthc[3] = {sxc[(SX3_DELTA + 21) * F], sxc[(SX3_DELTA + 22) * F], sxc[(SX3_DELTA + 23) * F]};
+      upd3_finish_b<4>(X, cg, rec, dth, dthc);
+    }
+    __syncthreads();  // U2 done
+  }
+  dump_rows();
+  __syncthreads();
+  store_tiles3<F, NTHR>(a, c, threadIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int F, int REG_S, int REG_C>
+__global__ void __launch_bounds__(128 + 8 * F, 1) eskf_kernel3(const __grid_constant__ KArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  using L = Lay3<F>;
+  constexpr int NTHR = 128 + 8 * F;
+  const int tid = threadIdx.x;
+  Ctx3 c;
+  c.smem = smem;
+  c.f0 = (int64_t)blockIdx.x * F;
+  c.nf = (int)((a.N - c.f0) < F ? (a.N - c.f0) : F);
+  c.gid0 = a.filter_id0 + c.f0;
+  c.traj = (a.n_traj > 1) ? (c.gid0 / a.filters_per_traj) : 0;
+  c.n_prop = a.n_prop ? a.n_prop + c.traj * a.E : nullptr;
+  c.dtp = a.dt ? a.dt + c.traj * a.T : nullptr;
+
+  // ---- covariance tiles and parameters (coalesced) ----
+  for (int idx = tid; idx < F * 576; idx += NTHR) {
+    const int f = idx / 576, r = idx - f * 576;
+    const int i = r / 24, j = r - i * 24;
+    smem[L::TB + f * TB3_STRIDE + i * RS3 + j] = (f < c.nf) ? a.P[(c.f0 + f) * 576 + r] : ((i == j) ? 1.0 : 0.0);
+  }
+  for (int idx = tid; idx < F * PAR_STRIDE; idx += NTHR) {
+    const int f = idx / PAR_STRIDE, r = idx - f * PAR_STRIDE;
+    const int64_t row = (f < c.nf) ? (c.f0 + f) : c.f0;
+    if (r < PAR_RD + 7) smem[L::SX + (SX3_QD + r) * F + f] = a.par[row * PAR_STRIDE + r];  // QD(13) then RD(7)
+  }
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp >= 4) {
+    reg_inc3<REG_C>();
+    role3_cov<F, NTHR>(a, c, tid - 128);
+  } else {
+    // (ptxas 12.9 crashes on kernels with more than one setmaxnreg.dec value, so all four scalar roles
+    // share REG_S although the Jacobian warp's sub-partition would have room for more)
+    reg_dec3<REG_S>();
+    if (warp == 0)
+      role3_imu<F, NTHR>(a, c, lane);
+    else if (warp == 1)
+      role3_cam<F, NTHR>(a, c, lane);
+    else if (warp == 2)
+      role3_stage<F, NTHR>(a, c, lane);
+    else
+      role3_jac<F, NTHR>(a, c, lane);
+  }
+}
+
+template <int F>
+cudaError_t launch_eskf_kernel3(const KArgs& a, cudaStream_t stream);
+
+}  // namespace eskf

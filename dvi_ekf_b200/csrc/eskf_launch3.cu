@@ -1,19 +1,19 @@
-// One translation unit per CTA shape of the v2 kernel: compiled with -DESKF_F=<filters per CTA>
+// One translation unit per CTA shape of the v3 kernel: compiled with -DESKF_F=<filters per CTA>
 // (see dvi_ekf_b200/build.py).  Shapes with more than 256 threads split the register file by role
-// with setmaxnreg (scalar warps ESKF_REG_S, covariance warps ESKF_REG_C registers per thread).
-// Registers live in the four SM sub-partitions (16,384 each) and warp w runs on sub-partition w % 4,
-// so with F = 28 (11 warps) sub-partitions 0..2 hold one scalar and two covariance warps: the kernel
-// launches with 168 registers per thread (3 x 32 x 168 <= 16,384) and the split must satisfy
-// REG_S + 2 REG_C <= 3 x 168 = 504, otherwise setmaxnreg.inc waits for ever.
-#include "eskf_kernel2.cuh"
+// with setmaxnreg (scalar warps ESKF_REG_S, covariance warps ESKF_REG_C registers per thread).  Registers live in the four SM sub-partitions (16,384 each) and warp w runs on
+// sub-partition w % 4, so with F = 28 (11 warps) sub-partitions 0..2 hold one scalar and two covariance
+// warps and sub-partition 3 the Jacobian warp and one covariance warp: the kernel launches with 168
+// registers per thread (3 x 32 x 168 <= 16,384) and the split must satisfy REG_S + 2 REG_C <= 504, otherwise
+// setmaxnreg.inc waits for ever.
+#include "eskf_kernel3.cuh"
 
 #ifndef ESKF_F
 #error "compile with -DESKF_F=<filters per CTA>"
 #endif
 #ifndef ESKF_REG_S
 #if ESKF_F > 16
-#define ESKF_REG_S 88
-#define ESKF_REG_C 208
+#define ESKF_REG_S 120
+#define ESKF_REG_C 192
 #else
 #define ESKF_REG_S 0
 #define ESKF_REG_C 0
@@ -23,14 +23,14 @@
 namespace eskf {
 
 template <>
-cudaError_t launch_eskf_kernel2<ESKF_F>(const KArgs& a, cudaStream_t stream) {
+cudaError_t launch_eskf_kernel3<ESKF_F>(const KArgs& a, cudaStream_t stream) {
   constexpr int F = ESKF_F;
   static_assert((8 * F) % 32 == 0, "covariance role must fill whole warps");
   static_assert(F <= 32, "one lane per filter in the scalar roles");
   static_assert(ESKF_REG_S == 0 || ESKF_REG_S + 2 * ESKF_REG_C <= 504, "register split exceeds a sub-partition");
-  constexpr size_t smem = (size_t)Lay2<F>::TOTAL * sizeof(double);
+  constexpr size_t smem = (size_t)Lay3<F>::TOTAL * sizeof(double);
   static_assert(smem <= 232448, "shared memory per CTA");
-  auto kern = eskf_kernel2<F, ESKF_REG_S, ESKF_REG_C>;
+  auto kern = eskf_kernel3<F, ESKF_REG_S, ESKF_REG_C>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)((a.N + F - 1) / F);

@@ -224,13 +224,11 @@ ESKF_HD void quat_about_axis(double angle, const double* axis, double* q) {
 struct ProbeTrig {
   double s1, c1, s2, c2, s3, c3, sd, cd;
   double ea3[3], eb3[3], ead[3], ebd[3];
+  double a1, a2, a3, ad;  // the angles the sines / cosines above belong to (probe_update)
 };
 
-ESKF_HD void probe_eval(const Model& m, const double* dofs, const double* notch, ProbeKin& k, ProbeTrig& t) {
-  sincos(dofs[0], &t.s1, &t.c1);
-  sincos(dofs[1], &t.s2, &t.c2);
-  sincos(dofs[2], &t.s3, &t.c3);
-  sincos(dofs[2] - notch[0], &t.sd, &t.cd);
+// products of the cached sines / cosines: triads, joint axis, p and R
+ESKF_HD void probe_assemble(const Model& m, const double* dofs, ProbeKin& k, ProbeTrig& t) {
   const double s1s2 = t.s1 * t.s2, c1s2 = t.c1 * t.s2;
   t.ea3[0] = s1s2 * t.s3 - t.c1 * t.c3;
   t.ea3[1] = t.s1 * t.c3 + c1s2 * t.s3;
@@ -255,6 +253,42 @@ ESKF_HD void probe_eval(const Model& m, const double* dofs, const double* notch,
     k.R[3 * i + 1] = m.sa * k.z6[i] + m.ca * t.ebd[i];
     k.R[3 * i + 2] = m.ca * k.z6[i] - m.sa * t.ebd[i];
   }
+}
+
+ESKF_HD void probe_eval(const Model& m, const double* dofs, const double* notch, ProbeKin& k, ProbeTrig& t) {
+  t.a1 = dofs[0];
+  t.a2 = dofs[1];
+  t.a3 = dofs[2];
+  t.ad = dofs[2] - notch[0];
+  sincos(t.a1, &t.s1, &t.c1);
+  sincos(t.a2, &t.s2, &t.c2);
+  sincos(t.a3, &t.s3, &t.c3);
+  sincos(t.ad, &t.sd, &t.cd);
+  probe_assemble(m, dofs, k, t);
+}
+
+// probe_eval for a (pk, t) that is valid for earlier (dofs, notch): only the sines / cosines whose angle
+// changed are evaluated again -- same inputs, same results as a full probe_eval.  Between camera updates
+// only the notch angle moves (equations.py:87), i.e. one sincos per step instead of four.
+ESKF_HD void probe_update(const Model& m, const double* dofs, const double* notch, ProbeKin& k, ProbeTrig& t) {
+  const double ad = dofs[2] - notch[0];
+  if (dofs[0] != t.a1) {
+    t.a1 = dofs[0];
+    sincos(t.a1, &t.s1, &t.c1);
+  }
+  if (dofs[1] != t.a2) {
+    t.a2 = dofs[1];
+    sincos(t.a2, &t.s2, &t.c2);
+  }
+  if (dofs[2] != t.a3) {
+    t.a3 = dofs[2];
+    sincos(t.a3, &t.s3, &t.c3);
+  }
+  if (ad != t.ad) {
+    t.ad = ad;
+    sincos(t.ad, &t.sd, &t.cd);
+  }
+  probe_assemble(m, dofs, k, t);
 }
 
 // dofs / notch part of f_predict (equations.py:87; Filter.py:243-245).  Returns true when the probe
@@ -335,7 +369,7 @@ ESKF_HD void propagate_scalar(const Model& m, Nominal& s, ProbeKin& pk, ProbeTri
 
   // ---- error Jacobians (Filter.py:249-342) with the buffered R_old / om_old / acc_old
   //      and the POST-predict dofs / notch ----
-  if (probe_changed) probe_eval(m, s.dofs, s.notch, pk, t);  // (pk, t) persist: same inputs, same kinematics
+  if (probe_changed) probe_update(m, s.dofs, s.notch, pk, t);  // (pk, t) persist: same inputs, same kinematics
   const double* Ro = s.R_old;
   fx[FX_DT] = dt;
   {  // A = (-R_old [acc_old]x) dt
@@ -879,22 +913,25 @@ ESKF_HD void joseph_rows_finish3(double* x, int r0, const double* up, const doub
 }
 
 // =====================================================================================
-// v2 kernel building blocks: the same arithmetic as propagate_scalar / fx_apply3, cut along
-// the lines of the warp-specialised kernel (eskf_kernel2.cuh): IMU nominal state, camera
-// nominal state, Jacobian blocks, and the covariance transform on a register-resident tile.
-// tests/hostcheck replays them on the CPU against propagate_scalar / fx_apply3.
+// Building blocks of the warp-specialised kernel (eskf_kernel3.cuh): the same arithmetic as
+// propagate_scalar, cut along the lines of its scalar roles -- IMU nominal state, camera nominal
+// state, Jacobian blocks.  The covariance algebra on the register-resident tile is in eskf_cov3.cuh.
+// tests/hostcheck replays them on the CPU against propagate_scalar / fx_apply3 and the oracle.
 // =====================================================================================
 
-// "fx2 record": Jacobian blocks laid out in the order the covariance role consumes them,
-// every row group starting on an even index so that it is fetched with 16-byte loads.
-constexpr int FX2_DT = 0;    // dt, pad
-constexpr int FX2_AB = 2;    // 3 x [A(i,0..2) B(i,0..2)]                     Fx[3:6,6:9], Fx[6:9,6:9]
-constexpr int FX2_R18 = 20;  // 3 x [C1(i,0..2) C2(i,0..5) pad]               Fx[18:21, 6:15]
-constexpr int FX2_R21 = 50;  // 3 x [D(i,0..3) E(i,0..2) pad]                 Fx[21:24, {9,10,11,15}], Fx[21:24,19:22]
-constexpr int FX2_NP = 74;   // 3x3 (+pad)  Fi[18:21,3:6]
-constexpr int FX2_NT = 84;   // 3x3 (+pad)  Fi[21:24,3:6]
-constexpr int FX2_SIZE = 94;
-constexpr int FX2_STRIDE = 94;
+// "fx3 record": Jacobian blocks in the order the covariance role consumes them.  Element (k, i) of a row
+// group lives at BASE + ROWS * k + i: the coefficients of one column k for all rows of the group are
+// adjacent, so that the group is applied column by column with 16-byte fetches.
+constexpr int FX3_DT = 0;    // dt, pad
+constexpr int FX3_H2 = 2;    // rows 21:24, 7 columns {9,10,11,15,19,20,21} x 3 rows (+1 pad):  D (4) then E (3)
+constexpr int FX3_H1 = 24;   // rows 18:21, 9 columns 6..14 x 3 rows (+1 pad):                 C1 (3) then C2 (6)
+constexpr int FX3_AB = 52;   // rows 3:9,   3 columns 6..8 x 6 rows:                           A rows then B rows
+constexpr int FX3_MAIN = 70; // everything below is always written
+constexpr int FX3_NP = 70;   // 3x3 (+pad)  Fi[18:21,3:6]   (only with IMU noise in Q, Filter.py:110-117)
+constexpr int FX3_NT = 80;   // 3x3 (+pad)  Fi[21:24,3:6]
+constexpr int FX3_SIZE = 90;
+constexpr int FX3_NPAIR = FX3_SIZE / 2;       // 45
+constexpr int FX3_NPAIR_MAIN = FX3_MAIN / 2;  // 35
 
 // Filter._predict_nominal, IMU part (equations.py:72-86; state.py:62-69): p, v, q.
 //   R_WB   rot(q) of the pre-step quaternion;  Rn_out  = rot(q+) (the new R_WB_old, Filter.py:227)
@@ -947,351 +984,225 @@ ESKF_HD void cam_nominal_step(double* pc, double* qc, const double* v_pre, const
   quat_from_matrix(Rc, qc);
 }
 
-// Filter._predict_error (Filter.py:249-342): Jacobian blocks in the fx2 layout, from the buffered
-// R_old / om_old / acc_old and the POST-predict (dofs, notch) whose probe kinematics are (pk, t).
-ESKF_HD void jacobian_blocks(const Model& m, const double* dofs, double notch_d, const ProbeKin& pk, const ProbeTrig& t,
-                             const double* Ro, double dt, const double* om_old, const double* acc_old,
-                             const double* sig_om, bool want_noise_jac, double* fx) {
-  fx[FX2_DT] = dt;
-  {  // A = (-R_old [acc_old]x) dt
-    double T[9];
-    mul_skew(Ro, acc_old, T);
+// ---- probe kinematics / trigonometry cache behind strided views ---------------------------------------
+// The Jacobian role keeps (pk, t) in shared memory, element-major over the filters of a CTA (stride ST);
+// with ST = 1 the same views sit on top of plain ProbeKin / ProbeTrig structs (host replay).
+template <int ST>
+struct PKView {  // ProbeKin: p(3) R(9) z6(3)
+  double* b;
+  ESKF_HD double& p(int i) const { return b[i * ST]; }
+  ESKF_HD double& R(int i) const { return b[(3 + i) * ST]; }
+  ESKF_HD double& z6(int i) const { return b[(12 + i) * ST]; }
+};
+template <int ST>
+struct TRView {  // ProbeTrig: s1 c1 s2 c2 s3 c3 sd cd ea3(3) eb3(3) ead(3) ebd(3) a1 a2 a3 ad
+  double* b;
+  ESKF_HD double& sc(int i) const { return b[i * ST]; }  // 0..7: s1 c1 s2 c2 s3 c3 sd cd
+  ESKF_HD double& ea3(int i) const { return b[(8 + i) * ST]; }
+  ESKF_HD double& eb3(int i) const { return b[(11 + i) * ST]; }
+  ESKF_HD double& ead(int i) const { return b[(14 + i) * ST]; }
+  ESKF_HD double& ebd(int i) const { return b[(17 + i) * ST]; }
+  ESKF_HD double& ang(int i) const { return b[(20 + i) * ST]; }  // a1 a2 a3 ad
+};
+constexpr int TR_SIZE = 24;
+constexpr int PK_SIZE = 15;
+static_assert(sizeof(ProbeTrig) == TR_SIZE * sizeof(double) && sizeof(ProbeKin) == PK_SIZE * sizeof(double), "view layout");
+
+// probe_update on views: the sines / cosines whose angle changed are evaluated again, everything that
+// depends on them is rebuilt into (pk, t).  Same arithmetic as probe_update / probe_assemble.
+template <int ST, int SP>
+ESKF_HD void probe_update_v(const Model& m, const double* dofs, const double* notch, const PKView<SP>& k, const TRView<ST>& t) {
+  const double ang[4] = {dofs[0], dofs[1], dofs[2], dofs[2] - notch[0]};
+  double sc[8];
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) fx[FX2_AB + 6 * i + k] = -T[3 * i + k] * dt;
+  for (int j = 0; j < 4; ++j) {
+    if (ang[j] != t.ang(j)) {
+      t.ang(j) = ang[j];
+      sincos(ang[j], &sc[2 * j], &sc[2 * j + 1]);
+      t.sc(2 * j) = sc[2 * j];
+      t.sc(2 * j + 1) = sc[2 * j + 1];
+    } else {
+      sc[2 * j] = t.sc(2 * j);
+      sc[2 * j + 1] = t.sc(2 * j + 1);
+    }
   }
-  {  // B = rot(normalise(quat(w=1, v=dt/2 om_old)))^T
-    double qo[4] = {0.5 * dt * om_old[0], 0.5 * dt * om_old[1], 0.5 * dt * om_old[2], 1.0};
-    quat_normalise(qo);
-    double Rb[9];
-    quat_to_rot(qo, Rb);
+  const double s1 = sc[0], c1 = sc[1], s2 = sc[2], c2 = sc[3], s3 = sc[4], c3 = sc[5], sd = sc[6], cd = sc[7];
+  const double s1s2 = s1 * s2, c1s2 = c1 * s2;
+  const double ea3[3] = {s1s2 * s3 - c1 * c3, s1 * c3 + c1s2 * s3, c2 * s3};
+  const double eb3[3] = {s1s2 * c3 + c1 * s3, c1s2 * c3 - s1 * s3, c2 * c3};
+  const double ead[3] = {s1s2 * sd - c1 * cd, s1 * cd + c1s2 * sd, c2 * sd};
+  const double ebd[3] = {s1s2 * cd + c1 * sd, c1s2 * cd - s1 * sd, c2 * cd};
+  const double z6[3] = {-s1 * c2, -c1 * c2, s2};
+  const double lq = m.L - dofs[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) fx[FX2_AB + 6 * i + 3 + j] = Rb[3 * j + i];
+  for (int i = 0; i < 3; ++i) {
+    t.ea3(i) = ea3[i];
+    t.eb3(i) = eb3[i];
+    t.ead(i) = ead[i];
+    t.ebd(i) = ebd[i];
+    k.z6(i) = z6[i];
+    k.p(i) = lq * z6[i] + dofs[4] * ea3[i] + dofs[5] * eb3[i];
+    k.R(3 * i + 0) = -ead[i];
+    k.R(3 * i + 1) = m.sa * z6[i] + m.ca * ebd[i];
+    k.R(3 * i + 2) = m.ca * z6[i] - m.sa * ebd[i];
   }
+}
+
+// Filter._predict_error (Filter.py:249-342): the Jacobian blocks in the fx3 layout, one function per row
+// group, from the buffered R_old / om_old / acc_old and the POST-predict (dofs, notch) whose probe
+// kinematics are (pk, t).  fx points at the whole FX3 record (registers: every index is a compile-time
+// constant); each function fills its own group.
+
+// rows 3:9 -- A = (-R_old [acc_old]x) dt and B = rot(normalise(quat(w=1, v=dt/2 om_old)))^T (Filter.py:132-134,255)
+ESKF_HD void jac_rows_ab(const double* Ro, double dt, const double* om_old, const double* acc_old, double* fx) {
+  double T[9];
+  mul_skew(Ro, acc_old, T);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) fx[FX3_AB + 6 * k + i] = -T[3 * i + k] * dt;
+  double qo[4] = {0.5 * dt * om_old[0], 0.5 * dt * om_old[1], 0.5 * dt * om_old[2], 1.0};
+  quat_normalise(qo);
+  double Rb[9];
+  quat_to_rot(qo, Rb);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) fx[FX3_AB + 6 * k + 3 + i] = Rb[3 * k + i];  // B(i, k) = Rb(k, i)
+}
+
+// dt pair + rows 21:24 -- D = dt d/dq{1,2,3,7} [R(q)^T om_tr] (R^T om_p is constant: no contribution) and
+// E = I - dt/2 [a + b]x, a = R_p^T (om_tr + om_p), b = R_p^T (om_old + om_p)
+template <int ST, int SP>
+ESKF_HD void jac_rows_h2(const Model& m, double notch_d, const PKView<SP>& pk, const TRView<ST>& t, double dt,
+                         const double* om_old, const double* sig_om, double* fx) {
+  fx[FX3_DT] = dt;
+  fx[FX3_DT + 1] = 0.0;
+  double wt[3];  // om_tr = om_old - sigma_om (noise symbols evaluated at sigma, quirk Q6)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) wt[i] = om_old[i] - sig_om[i];
+  const double sd = t.sc(6), cd = t.sc(7);
+  const double z6[3] = {pk.z6(0), pk.z6(1), pk.z6(2)};
+  {
+    const double ead[3] = {t.ead(0), t.ead(1), t.ead(2)}, ebd[3] = {t.ebd(0), t.ebd(1), t.ebd(2)};
+    const double al = dot3(ead, wt), be = dot3(ebd, wt), ze = dot3(z6, wt);
+    const double al1 = ead[1] * wt[0] - ead[0] * wt[1];
+    const double be1 = ebd[1] * wt[0] - ebd[0] * wt[1];
+    const double ze1 = z6[1] * wt[0] - z6[0] * wt[1];
+    const double al2 = -sd * ze, be2 = -cd * ze, ze2 = sd * al + cd * be;
+    double* D = fx + FX3_H2;  // D(i, k) at D[3 * k + i]; rows: (-alpha, sa zeta + ca beta, ca zeta - sa beta)
+    D[0] = dt * (-al1);
+    D[1] = dt * (m.sa * ze1 + m.ca * be1);
+    D[2] = dt * (m.ca * ze1 - m.sa * be1);
+    D[3] = dt * (-al2);
+    D[4] = dt * (m.sa * ze2 + m.ca * be2);
+    D[5] = dt * (m.ca * ze2 - m.sa * be2);
+    // d/dq3: alpha' = beta, beta' = -alpha, zeta' = 0 ; d/dq7 = - d/dq3
+    D[6] = dt * (-be);
+    D[7] = dt * (-m.ca * al);
+    D[8] = dt * (m.sa * al);
+    D[9] = -D[6];
+    D[10] = -D[7];
+    D[11] = -D[8];
+  }
+  {
+    double ua[3], ub[3], a[3], b[3], R[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = pk.R(i);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double omp = z6[i] * notch_d;
+      ua[i] = wt[i] + omp;
+      ub[i] = om_old[i] + omp;
+    }
+    mtv3(R, ua, a);
+    mtv3(R, ub, b);
+    const double h = 0.5 * dt;
+    const double e0 = h * (a[0] + b[0]), e1 = h * (a[1] + b[1]), e2 = h * (a[2] + b[2]);
+    double* E = fx + FX3_H2 + 12;  // E(i, k) at E[3 * k + i]
+    E[0] = 1.0;
+    E[1] = -e2;
+    E[2] = e1;
+    E[3] = e2;
+    E[4] = 1.0;
+    E[5] = -e0;
+    E[6] = -e1;
+    E[7] = e0;
+    E[8] = 1.0;
+    fx[FX3_H2 + 21] = 0.0;
+  }
+}
+
+// rows 18:21 -- C1 = -dt R_old [w]x, w = p + om_tr x p (v_tr = p_tr, quirk Q2) and
+// C2 = dt R_old (I + [om_tr]x) dp/dq(1..6)
+template <int ST, int SP>
+ESKF_HD void jac_rows_h1(const Model& m, const double* dofs, const PKView<SP>& pk, const TRView<ST>& t, const double* Ro,
+                         double dt, const double* om_old, const double* sig_om, double* fx) {
   double wt[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) wt[i] = om_old[i] - sig_om[i];
-  {  // C1 = -dt R_old [w]x,  w = p + om_tr x p
+  const double p[3] = {pk.p(0), pk.p(1), pk.p(2)};
+  {
     double w[3], T[9];
-    cross3(wt, pk.p, w);
+    cross3(wt, p, w);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) w[i] = pk.p[i] + w[i];
+    for (int i = 0; i < 3; ++i) w[i] = p[i] + w[i];
     mul_skew(Ro, w, T);
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int k = 0; k < 3; ++k) fx[FX2_R18 + 10 * i + k] = -dt * T[3 * i + k];
+      for (int k = 0; k < 3; ++k) fx[FX3_H1 + 3 * k + i] = -dt * T[3 * i + k];
   }
-  {  // C2 = dt R_old (I + [om_tr]x) dp/dq(1..6)
-    double Mw[9], S[9];
-    mul_skew(Ro, wt, S);
+  double Mw[9], S[9];
+  mul_skew(Ro, wt, S);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Mw[i] = dt * (Ro[i] + S[i]);
-    const double lq = m.L - dofs[3];
-    const double dz2[3] = {t.s1 * t.s2, t.c1 * t.s2, t.c2};
-    const double k2 = dofs[4] * t.s3 + dofs[5] * t.c3;
-    double col[6][3];
-    col[0][0] = pk.p[1];
-    col[0][1] = -pk.p[0];
-    col[0][2] = 0.0;
+  for (int i = 0; i < 9; ++i) Mw[i] = dt * (Ro[i] + S[i]);
+  const double s1 = t.sc(0), c1 = t.sc(1), s2 = t.sc(2), c2 = t.sc(3), s3 = t.sc(4), c3 = t.sc(5);
+  const double lq = m.L - dofs[3];
+  const double dz2[3] = {s1 * s2, c1 * s2, c2};  // d z6 / d q2
+  const double k2 = dofs[4] * s3 + dofs[5] * c3;
+  double col[3];
+  col[0] = p[1];
+  col[1] = -p[0];
+  col[2] = 0.0;
+  mv3(Mw, col, fx + FX3_H1 + 9);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      col[1][i] = lq * dz2[i] - k2 * pk.z6[i];
-      col[2][i] = dofs[4] * t.eb3[i] - dofs[5] * t.ea3[i];
-      col[3][i] = -pk.z6[i];
-      col[4][i] = t.ea3[i];
-      col[5][i] = t.eb3[i];
-    }
+  for (int i = 0; i < 3; ++i) col[i] = lq * dz2[i] - k2 * pk.z6(i);
+  mv3(Mw, col, fx + FX3_H1 + 12);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      double y[3];
-      mv3(Mw, col[k], y);
-      fx[FX2_R18 + 0 * 10 + 3 + k] = y[0];
-      fx[FX2_R18 + 1 * 10 + 3 + k] = y[1];
-      fx[FX2_R18 + 2 * 10 + 3 + k] = y[2];
-    }
-  }
-  {  // D = dt d/dq{1,2,3,7} [ R(q)^T om_tr ]
-    const double al = dot3(t.ead, wt), be = dot3(t.ebd, wt), ze = dot3(pk.z6, wt);
-    const double al1 = t.ead[1] * wt[0] - t.ead[0] * wt[1];
-    const double be1 = t.ebd[1] * wt[0] - t.ebd[0] * wt[1];
-    const double ze1 = pk.z6[1] * wt[0] - pk.z6[0] * wt[1];
-    const double al2 = -t.sd * ze, be2 = -t.cd * ze, ze2 = t.sd * al + t.cd * be;
-    double* D0 = fx + FX2_R21;
-    double* D1 = fx + FX2_R21 + 8;
-    double* D2 = fx + FX2_R21 + 16;
-    D0[0] = dt * (-al1);
-    D1[0] = dt * (m.sa * ze1 + m.ca * be1);
-    D2[0] = dt * (m.ca * ze1 - m.sa * be1);
-    D0[1] = dt * (-al2);
-    D1[1] = dt * (m.sa * ze2 + m.ca * be2);
-    D2[1] = dt * (m.ca * ze2 - m.sa * be2);
-    D0[2] = dt * (-be);
-    D1[2] = dt * (-m.ca * al);
-    D2[2] = dt * (m.sa * al);
-    D0[3] = -D0[2];
-    D1[3] = -D1[2];
-    D2[3] = -D2[2];
-  }
-  {  // E = I - dt/2 [a + b]x
-    double ua[3], ub[3], a[3], b[3];
+  for (int i = 0; i < 3; ++i) col[i] = dofs[4] * t.eb3(i) - dofs[5] * t.ea3(i);
+  mv3(Mw, col, fx + FX3_H1 + 15);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const double omp = pk.z6[i] * notch_d;
-      ua[i] = wt[i] + omp;
-      ub[i] = om_old[i] + omp;
-    }
-    mtv3(pk.R, ua, a);
-    mtv3(pk.R, ub, b);
-    const double h = 0.5 * dt;
-    const double e0 = h * (a[0] + b[0]), e1 = h * (a[1] + b[1]), e2 = h * (a[2] + b[2]);
-    double* E0 = fx + FX2_R21 + 4;
-    double* E1 = fx + FX2_R21 + 8 + 4;
-    double* E2 = fx + FX2_R21 + 16 + 4;
-    E0[0] = 1.0;
-    E0[1] = e2;
-    E0[2] = -e1;
-    E1[0] = -e2;
-    E1[1] = 1.0;
-    E1[2] = e0;
-    E2[0] = e1;
-    E2[1] = -e0;
-    E2[2] = 1.0;
-  }
-  if (want_noise_jac) {
-    double T[9];
-    mul_skew(Ro, pk.p, T);
+  for (int i = 0; i < 3; ++i) col[i] = -pk.z6(i);
+  mv3(Mw, col, fx + FX3_H1 + 18);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) fx[FX2_NP + i] = dt * T[i];
+  for (int i = 0; i < 3; ++i) col[i] = t.ea3(i);
+  mv3(Mw, col, fx + FX3_H1 + 21);
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) fx[FX2_NT + 3 * i + j] = -dt * pk.R[3 * j + i];
-  }
+  for (int i = 0; i < 3; ++i) col[i] = t.eb3(i);
+  mv3(Mw, col, fx + FX3_H1 + 24);
+  fx[FX3_H1 + 27] = 0.0;
 }
 
-// X <- Fx X for three 24-vectors held in registers (X[i][v] = element i of vector v): the sparse
-// transition matrix of Filter._predict_error applied as straight-line code.  Both covariance passes
-// of a step use this one function (column tile of P, then row tile of Fx P), see eskf_kernel2.cuh.
-// Coefficients come from the fx2 record through 16-byte loads.
+// rows 18:24 of Fi (only matter when Q[3:6] != 0, Filter.py:110-117)
+template <int SP>
+ESKF_HD void jac_rows_noise(const PKView<SP>& pk, const double* Ro, double dt, double* fx) {
+  double T[9];
+  const double p[3] = {pk.p(0), pk.p(1), pk.p(2)};
+  mul_skew(Ro, p, T);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) fx[FX3_NP + i] = dt * T[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) fx[FX3_NT + 3 * i + j] = -dt * pk.R(3 * j + i);
+  fx[FX3_NP + 9] = 0.0;
+  fx[FX3_NT + 9] = 0.0;
+}
+
+// 16-byte coefficient pairs of the fx3 record
 struct alignas(16) d2 {
   double x, y;
 };
-// PS = stride between consecutive coefficient pairs of one record (1: plain array; F: the
-// [pair][filter] layout of the v2 kernel, conflict free for writer and readers).
-template <int PS>
-ESKF_HD double fx2_at(const d2* f2, int j) {
-  const d2 v = f2[(j >> 1) * PS];
-  return (j & 1) ? v.y : v.x;
-}
-template <int PS>
-ESKF_HD void fx_apply_reg(double (&X)[24][3], const d2* fx2) {
-  const d2* f2 = fx2;
-  const double dt = f2[(FX2_DT / 2) * PS].x;
-  double y18[3][3], y21[3][3];
-  // rows 18:21 (camera position error)
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const d2 c0 = f2[((FX2_R18 + 10 * i) / 2 + 0) * PS], c1 = f2[((FX2_R18 + 10 * i) / 2 + 1) * PS], c2 = f2[((FX2_R18 + 10 * i) / 2 + 2) * PS],
-             c3 = f2[((FX2_R18 + 10 * i) / 2 + 3) * PS], c4 = f2[((FX2_R18 + 10 * i) / 2 + 4) * PS];
-    const double c[9] = {c0.x, c0.y, c1.x, c1.y, c2.x, c2.y, c3.x, c3.y, c4.x};
-#pragma unroll
-    for (int v = 0; v < 3; ++v) {
-      double y = dt * X[3 + i][v];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) y += c[k] * X[6 + k][v];  // C1 on theta (6:9), C2 on dofs (9:15)
-      y18[i][v] = y + X[16 + i][v];                          // mis-aligned identity block (quirk Q3)
-    }
-  }
-  // rows 21:24 (camera orientation error)
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const d2 c0 = f2[((FX2_R21 + 8 * i) / 2 + 0) * PS], c1 = f2[((FX2_R21 + 8 * i) / 2 + 1) * PS], c2 = f2[((FX2_R21 + 8 * i) / 2 + 2) * PS],
-             c3 = f2[((FX2_R21 + 8 * i) / 2 + 3) * PS];
-#pragma unroll
-    for (int v = 0; v < 3; ++v) {
-      double y = (i == 0) ? 0.0 : X[21 + i][v];  // Fx[22,22] = Fx[23,23] = 1
-      y += c0.x * X[9][v];
-      y += c0.y * X[10][v];
-      y += c1.x * X[11][v];
-      y += c1.y * X[15][v];
-      y += c2.x * X[19][v];
-      y += c2.y * X[20][v];
-      y += c3.x * X[21][v];
-      y21[i][v] = y;
-    }
-  }
-  // rows 0:3  p += dt v
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int v = 0; v < 3; ++v) X[i][v] = X[i][v] + dt * X[3 + i][v];
-  // rows 3:6  v += A theta ; rows 6:9  theta = B theta
-  {
-    double yt[3][3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const d2 c0 = f2[((FX2_AB + 6 * i) / 2 + 0) * PS], c1 = f2[((FX2_AB + 6 * i) / 2 + 1) * PS], c2 = f2[((FX2_AB + 6 * i) / 2 + 2) * PS];
-#pragma unroll
-      for (int v = 0; v < 3; ++v) {
-        double yv = X[3 + i][v];
-        yv += c0.x * X[6][v];
-        yv += c0.y * X[7][v];
-        yv += c1.x * X[8][v];
-        X[3 + i][v] = yv;
-        double t = 0.0;
-        t += c1.y * X[6][v];
-        t += c2.x * X[7][v];
-        t += c2.y * X[8][v];
-        yt[i][v] = t;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int v = 0; v < 3; ++v) X[6 + i][v] = yt[i][v];
-  }
-  // rows 15:17 notch chain
-#pragma unroll
-  for (int v = 0; v < 3; ++v) {
-    X[15][v] = X[15][v] + dt * X[16][v];
-    X[16][v] = X[16][v] + dt * X[17][v];
-  }
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int v = 0; v < 3; ++v) {
-      X[18 + i][v] = y18[i][v];
-      X[21 + i][v] = y21[i][v];
-    }
-}
-
-// Pass 1 of a covariance step: T(:, tile) = Fx X, every finished row stored straight away as
-// out[i * OS + v] (no in-place update: X is dead after this pass, the next pass starts from the
-// transposed tile).  Interleaving the 72 stores with the FMAs lets the shared-memory pipe and the FP64
-// pipe overlap inside one warp.
-template <int PS, int OS>
-ESKF_HD void fx_apply_store(const double (&X)[24][3], const d2* f2, double* out) {
-  const double dt = f2[(FX2_DT / 2) * PS].x;
-  // untouched rows (identity rows of Fx): dofs 9:15 and notch'' 17
-#pragma unroll
-  for (int i = 9; i < 15; ++i)
-#pragma unroll
-    for (int v = 0; v < 3; ++v) out[i * OS + v] = X[i][v];
-#pragma unroll
-  for (int v = 0; v < 3; ++v) out[17 * OS + v] = X[17][v];
-  // rows 18:21 (camera position error)
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const d2 c0 = f2[((FX2_R18 + 10 * i) / 2 + 0) * PS], c1 = f2[((FX2_R18 + 10 * i) / 2 + 1) * PS],
-             c2 = f2[((FX2_R18 + 10 * i) / 2 + 2) * PS], c3 = f2[((FX2_R18 + 10 * i) / 2 + 3) * PS],
-             c4 = f2[((FX2_R18 + 10 * i) / 2 + 4) * PS];
-    const double c[9] = {c0.x, c0.y, c1.x, c1.y, c2.x, c2.y, c3.x, c3.y, c4.x};
-    double y[3];
-#pragma unroll
-    for (int v = 0; v < 3; ++v) y[v] = dt * X[3 + i][v];
-#pragma unroll
-    for (int k = 0; k < 9; ++k)
-#pragma unroll
-      for (int v = 0; v < 3; ++v) y[v] += c[k] * X[6 + k][v];
-#pragma unroll
-    for (int v = 0; v < 3; ++v) out[(18 + i) * OS + v] = y[v] + X[16 + i][v];
-  }
-  // rows 21:24 (camera orientation error)
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const d2 c0 = f2[((FX2_R21 + 8 * i) / 2 + 0) * PS], c1 = f2[((FX2_R21 + 8 * i) / 2 + 1) * PS],
-             c2 = f2[((FX2_R21 + 8 * i) / 2 + 2) * PS], c3 = f2[((FX2_R21 + 8 * i) / 2 + 3) * PS];
-    double y[3];
-#pragma unroll
-    for (int v = 0; v < 3; ++v) {
-      y[v] = (i == 0) ? 0.0 : X[21 + i][v];
-      y[v] += c0.x * X[9][v];
-    }
-#pragma unroll
-    for (int v = 0; v < 3; ++v) y[v] += c0.y * X[10][v];
-#pragma unroll
-    for (int v = 0; v < 3; ++v) y[v] += c1.x * X[11][v];
-#pragma unroll
-    for (int v = 0; v < 3; ++v) y[v] += c1.y * X[15][v];
-#pragma unroll
-    for (int v = 0; v < 3; ++v) y[v] += c2.x * X[19][v];
-#pragma unroll
-    for (int v = 0; v < 3; ++v) y[v] += c2.y * X[20][v];
-#pragma unroll
-    for (int v = 0; v < 3; ++v) out[(21 + i) * OS + v] = y[v] + c3.x * X[21][v];
-  }
-  // rows 0:3  p += dt v
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int v = 0; v < 3; ++v) out[i * OS + v] = X[i][v] + dt * X[3 + i][v];
-  // rows 3:6  v += A theta ; rows 6:9  theta = B theta
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const d2 c0 = f2[((FX2_AB + 6 * i) / 2 + 0) * PS], c1 = f2[((FX2_AB + 6 * i) / 2 + 1) * PS],
-             c2 = f2[((FX2_AB + 6 * i) / 2 + 2) * PS];
-#pragma unroll
-    for (int v = 0; v < 3; ++v) {
-      double yv = X[3 + i][v];
-      yv += c0.x * X[6][v];
-      yv += c0.y * X[7][v];
-      yv += c1.x * X[8][v];
-      out[(3 + i) * OS + v] = yv;
-      double t = 0.0;
-      t += c1.y * X[6][v];
-      t += c2.x * X[7][v];
-      t += c2.y * X[8][v];
-      out[(6 + i) * OS + v] = t;
-    }
-  }
-  // rows 15:17 notch chain
-#pragma unroll
-  for (int v = 0; v < 3; ++v) {
-    out[15 * OS + v] = X[15][v] + dt * X[16][v];
-    out[16 * OS + v] = X[16][v] + dt * X[17][v];
-  }
-}
-
-// Fi Q Fi^T for the row tile of lane group g (X[j][v] = P'[3g+v][j]); Filter.py:349.
-template <int PS, typename QD>
-ESKF_HD void process_noise_reg(double (&X)[24][3], int g, const d2* f2, const QD& qd, bool imu_q) {
-  // diagonal: rows 3..14 get qd[r-3] (Fi[3:15,0:12] = I), row 17 gets qd(12) (Fi[17,12] = 1)
-#pragma unroll
-  for (int r = 3; r < 15; ++r)
-    if (g == r / 3) X[r][r % 3] += qd(r - 3);
-  if (g == 5) X[17][2] += qd(12);
-  if (imu_q && (g == 2 || g == 6 || g == 7)) {
-    // n_om drives theta (I), p_C (Np) and theta_C (Nt): L Q_om L^T on rows/cols {6:9,18:21,21:24};
-    // the diagonal of the theta block was added above.
-    double Lr[3][3];
-#pragma unroll
-    for (int v = 0; v < 3; ++v)
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        Lr[v][k] = (g == 2) ? ((k == v) ? 1.0 : 0.0) : (g == 6) ? fx2_at<PS>(f2, FX2_NP + 3 * v + k) : fx2_at<PS>(f2, FX2_NT + 3 * v + k);
-#pragma unroll
-    for (int cb = 0; cb < 3; ++cb) {
-      const int c0 = (cb == 0) ? 6 : (cb == 1) ? 18 : 21;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        double Lc[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          Lc[k] = (cb == 0) ? ((k == j) ? 1.0 : 0.0) : (cb == 1) ? fx2_at<PS>(f2, FX2_NP + 3 * j + k) : fx2_at<PS>(f2, FX2_NT + 3 * j + k);
-#pragma unroll
-        for (int v = 0; v < 3; ++v) {
-          double acc = 0.0;
-#pragma unroll
-          for (int k = 0; k < 3; ++k) acc += Lr[v][k] * qd(3 + k) * Lc[k];
-          if (!(g == 2 && cb == 0)) X[c0 + j][v] += acc;
-        }
-      }
-    }
-  }
-}
 
 }  // namespace eskf

@@ -3,8 +3,16 @@
 // dvi_ekf/models/trajectory/ImuTrajectory.py:133).  Philox4x32-10 keyed by the
 // run seed, counter = (step, kind*16 + draw, filter id lo, filter id hi), so a
 // filter's noise depends only on its GLOBAL id: results are independent of how
-// the batch is sharded over CTAs or GPUs.  Box-Muller in FP64 so that the
-// numpy replica in tests/ reproduces the stream to rounding.
+// the batch is sharded over CTAs or GPUs.
+//
+// One Philox block = four 32-bit uniforms = two Box-Muller pairs = four standard
+// normals, evaluated in single precision (the construction of curand_normal:
+// 32-bit uniforms, r = sqrt(-2 ln u1), angle = 2 pi u2) and widened to FP64.  On
+// the device the logarithm / sine / cosine are the SFU approximations (MUFU),
+// which is what keeps the generator off the FP64 pipe the filter lives on; the
+// noise a run used is therefore defined by the device and can be read back
+// with eskf_noise_dump() (include/eskf.h) -- the parity tests feed exactly those
+// samples to the oracle.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -19,9 +27,8 @@
 
 namespace eskf {
 
-constexpr uint32_t RNG_KIND_IMU = 1;   // 6 normals per IMU step
-constexpr uint32_t RNG_KIND_CAM = 2;   // 6 normals per camera update (position, orientation)
-constexpr uint32_t RNG_KIND_CAM2 = 3;  // 2 normals per camera update (notch, spare)
+constexpr uint32_t RNG_KIND_IMU = 1;  // 6 normals per IMU step      (draw 0: om xyz + acc x, draw 1: acc yz)
+constexpr uint32_t RNG_KIND_CAM = 2;  // 7 normals per camera update (draw 0: position + theta x, draw 1: theta yz, notch)
 
 ESKF_HD void philox4x32_10(uint32_t* c, uint32_t k0, uint32_t k1) {
 #pragma unroll
@@ -41,29 +48,34 @@ ESKF_HD void philox4x32_10(uint32_t* c, uint32_t k0, uint32_t k1) {
   }
 }
 
-// two standard normals from one Philox block
-ESKF_HD void normal_pair(uint64_t seed, uint64_t filter, uint64_t step, uint32_t kind, uint32_t draw, double* z) {
+// Box-Muller on two 32-bit words: u1 in (0, 1], angle in [-pi, pi)
+ESKF_HD void box_muller32(uint32_t a, uint32_t b, double* z) {
+  const float u1 = (float)a * 2.3283064365386963e-10f + 1.1641532182693481e-10f;  // a 2^-32 + 2^-33
+  const float th = (float)(int32_t)b * 1.4629180792671596e-9f;                     // b pi 2^-31
+#ifdef __CUDA_ARCH__
+  const float r = sqrtf(-2.0f * __logf(u1));
+  const float s = __sinf(th), c = __cosf(th);
+#else
+  const float r = sqrtf(-2.0f * logf(u1));
+  const float s = sinf(th), c = cosf(th);
+#endif
+  z[0] = (double)(r * c);
+  z[1] = (double)(r * s);
+}
+
+// four standard normals from one Philox block
+ESKF_HD void normal4(uint64_t seed, uint64_t filter, uint64_t step, uint32_t kind, uint32_t draw, double* z) {
   uint32_t c[4] = {(uint32_t)step, kind * 16u + draw + ((uint32_t)(step >> 32) << 8), (uint32_t)filter,
                    (uint32_t)(filter >> 32)};
   philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-  const uint64_t a = ((uint64_t)c[1] << 32) | c[0];
-  const uint64_t b = ((uint64_t)c[3] << 32) | c[2];
-  const double u1 = ((double)(a >> 11) + 0.5) * 1.1102230246251565e-16;  // (0,1)
-  const double u2 = ((double)(b >> 11) + 0.5) * 1.1102230246251565e-16;
-  const double r = sqrt(-2.0 * log(u1));
-  double s, co;
-  sincos(6.283185307179586476925286766559 * u2, &s, &co);
-  z[0] = r * co;
-  z[1] = r * s;
+  box_muller32(c[0], c[1], z);
+  box_muller32(c[2], c[3], z + 2);
 }
 
-ESKF_HD void normal6(uint64_t seed, uint64_t filter, uint64_t step, uint32_t kind, double* z) {
-  normal_pair(seed, filter, step, kind, 0, z);
-  normal_pair(seed, filter, step, kind, 1, z + 2);
-  normal_pair(seed, filter, step, kind, 2, z + 4);
-}
-ESKF_HD void normal2(uint64_t seed, uint64_t filter, uint64_t step, uint32_t kind, double* z) {
-  normal_pair(seed, filter, step, kind, 0, z);
+// z[0..7]: eight normals of (filter, step, kind); the IMU stream uses z[0..5], the camera stream z[0..6]
+ESKF_HD void normal8(uint64_t seed, uint64_t filter, uint64_t step, uint32_t kind, double* z) {
+  normal4(seed, filter, step, kind, 0, z);
+  normal4(seed, filter, step, kind, 1, z + 4);
 }
 
 }  // namespace eskf

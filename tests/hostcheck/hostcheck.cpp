@@ -3,7 +3,7 @@
 // what one CTA does for one filter: the scalar role followed by the eight
 // covariance lanes (column pass, then row pass).  Lets the not-gpu test suite
 // check the device arithmetic against the oracle without a GPU.
-#include "../../dvi_ekf_b200/csrc/eskf_math.cuh"
+#include "../../dvi_ekf_b200/csrc/eskf_cov3.cuh"
 #include <string.h>
 
 using namespace eskf;
@@ -72,9 +72,9 @@ int hc_update(const double* model, double* x, double* P, const double* u, const 
   return 1;
 }
 
-// The same step through the building blocks of the v2 kernel (eskf_kernel2.cuh): split scalar roles,
-// register tile X <- Fx X, transposition, X <- Fx X, process noise.
-void hc_propagate2(const double* model, double* x, double* P, double* u, double* Ro, double dt, const double* om_acc,
+// The same step through the building blocks of the warp-specialised kernel (eskf_kernel3.cuh): split scalar
+// roles, Jacobian row groups on strided views, register tile: T = Fx X stored, transposition, X <- Fx X, process noise.
+void hc_propagate3(const double* model, double* x, double* P, double* u, double* Ro, double dt, const double* om_acc,
                    const double* qd, const double* sig_om, double* fx_out) {
   Model m{model[0], sin(model[1]), cos(model[1]), (int)model[2], (int)model[3]};
   Nominal s; load_nominal(s, x, u, Ro);
@@ -85,32 +85,78 @@ void hc_propagate2(const double* model, double* x, double* P, double* u, double*
   // CAMERA role (pre-step v, R_WB, probe kinematics, notch')
   cam_nominal_step(s.pc, s.qc, s.v, R_WB, dt, s.om_old, om_acc, pk.p, pk.R, pk.z6, s.notch[1]);
   // JACOB role
-  alignas(16) double fx[FX2_SIZE];
-  for (int i = 0; i < FX2_SIZE; ++i) fx[i] = 0.0;
-  if (dofs_notch_step(m, s.dofs, s.notch, dt)) probe_eval(m, s.dofs, s.notch, pk, t);
-  jacobian_blocks(m, s.dofs, s.notch[1], pk, t, s.R_old, dt, s.om_old, s.acc_old, sig_om, imu_q, fx);
+  alignas(16) double fx3[FX3_SIZE];
+  for (int i = 0; i < FX3_SIZE; ++i) fx3[i] = 0.0;
+  const PKView<1> pkv{reinterpret_cast<double*>(&pk)};
+  const TRView<1> trv{reinterpret_cast<double*>(&t)};
+  if (dofs_notch_step(m, s.dofs, s.notch, dt)) probe_update_v(m, s.dofs, s.notch, pkv, trv);
+  jac_rows_h2(m, s.notch[1], pkv, trv, dt, s.om_old, sig_om, fx3);
+  jac_rows_h1(m, s.dofs, pkv, trv, s.R_old, dt, s.om_old, sig_om, fx3);
+  if (imu_q) jac_rows_noise(pkv, s.R_old, dt, fx3);
+  jac_rows_ab(s.R_old, dt, s.om_old, s.acc_old, fx3);  // (IMU role)
   // IMU role
   double Rn[9];
   imu_nominal_step(s.p, s.v, s.q, R_WB, dt, s.om_old, s.acc_old, om_acc, om_acc + 3, Rn);
   for (int i = 0; i < 9; ++i) s.R_old[i] = Rn[i];
   for (int i = 0; i < 3; ++i) { s.om_old[i] = om_acc[i]; s.acc_old[i] = om_acc[3 + i]; }
   // COVARIANCE role: eight lanes, tile of three columns each
-  const d2* f2 = reinterpret_cast<const d2*>(fx);
+  const d2* f2 = reinterpret_cast<const d2*>(fx3);
   static double X[8][24][3];
   double T[24][24];
   for (int g = 0; g < 8; ++g) {
     for (int i = 0; i < 24; ++i) for (int v = 0; v < 3; ++v) X[g][i][v] = P[i * 24 + 3 * g + v];
-    fx_apply_store<1, 24>(X[g], f2, &T[0][0] + 3 * g);
+    fx3_apply_store<1, 24>(X[g], f2, &T[0][0] + 3 * g);
   }
   auto qdf = [&](int j) { return qd[j]; };
   for (int g = 0; g < 8; ++g) {
     for (int k = 0; k < 24; ++k) for (int v = 0; v < 3; ++v) X[g][k][v] = T[3 * g + v][k];
-    fx_apply_reg<1>(X[g], f2);
-    process_noise_reg<1>(X[g], g, f2, qdf, imu_q);
+    fx3_apply_inplace<1>(X[g], f2);
+    double qdv[3];
+    fx3_noise_diag(g, qdf, qdv);
+    fx3_process_noise<1>(X[g], g, f2, qdv, qdf, imu_q);
     for (int j = 0; j < 24; ++j) for (int v = 0; v < 3; ++v) P[(3 * g + v) * 24 + j] = X[g][j][v];
   }
   store_nominal(s, x, u, Ro);
-  if (fx_out) memcpy(fx_out, fx, sizeof(double) * FX2_SIZE);
+  if (fx_out) memcpy(fx_out, fx3, sizeof(double) * FX3_SIZE);
+}
+
+// Filter.update through the register-tile building blocks of eskf_kernel3.cuh: the eight lanes of a filter
+// replayed phase by phase around the u3 exchange record (warp-level synchronisation points = loop boundaries).
+int hc_update3(const double* model, double* x, double* P, const double* u, const double* Ro, const double* cam /*pos3 quat4*/,
+               double notch, const double* rd, double* K_out) {
+  Model m{model[0], sin(model[1]), cos(model[1]), (int)model[2], (int)model[3]};
+  Nominal s; double uu[6], RR[9]; memcpy(uu, u, 48); memcpy(RR, Ro, 72);
+  load_nominal(s, x, uu, RR);
+  static double X[8][24][3];
+  for (int g = 0; g < 8; ++g)
+    for (int i = 0; i < 24; ++i) for (int v = 0; v < 3; ++v) X[g][i][v] = P[(3 * g + v) * 24 + i];  // rows used as columns
+  alignas(16) double rec[U3_SIZE];
+  for (int g = 0; g < 8; ++g) upd3_publish_S<1>(X[g], g, rd, rec);
+  double S[49], Si[49];
+  for (int j = 0; j < 49; ++j) S[j] = rec[U3_S + j];
+  bool ok = inv7(S, Si);
+  for (int j = 0; j < 49; ++j) rec[U3_SINV + j] = Si[j];
+  double res[7];
+  ok = update_residual(s, cam, cam + 3, notch, res) && ok;
+  if (!ok) return 0;
+  double K[8][3][7], delta[24];
+  for (int g = 0; g < 8; ++g) {
+    double dl[3];
+    upd3_gain<1>(X[g], g, rec, res, rd, K[g], dl);
+    for (int v = 0; v < 3; ++v) delta[3 * g + v] = dl[v];
+  }
+  inject_error(m, s, delta);
+  for (int g = 0; g < 8; ++g) upd3_w_pass<1>(X[g], g, rec);
+  for (int g = 0; g < 8; ++g) {
+    upd3_finish_a<1>(X[g], g, rec);
+    upd3_finish_b<1>(X[g], g, rec, delta + 6, delta + 21);
+  }
+  for (int g = 0; g < 8; ++g)
+    for (int i = 0; i < 24; ++i) for (int v = 0; v < 3; ++v) P[(3 * g + v) * 24 + i] = X[g][i][v];
+  store_nominal(s, x, uu, RR);
+  if (K_out)
+    for (int g = 0; g < 8; ++g) for (int v = 0; v < 3; ++v) for (int mm = 0; mm < 7; ++mm) K_out[7 * (3 * g + v) + mm] = K[g][v][mm];
+  return 1;
 }
 
 }  // extern "C"

@@ -10,9 +10,9 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-9  # north-star: nominal state, error state and P within 1e-9 relative per step (FP64)
 
 
-@pytest.fixture(scope="module", params=[2, 1], ids=["kernel2", "kernel1"])
+@pytest.fixture(scope="module", params=[3, 1], ids=["kernel3", "kernel1"])
 def BatchFilter(request):
-    """the engine class bound to one kernel variant (2 = warp-specialised default, 1 = first kernel)"""
+    """the engine class bound to one kernel variant (3 = warp-specialised default, 1 = first kernel)"""
     import functools
 
     from dvi_ekf_b200 import BatchFilter as BF

@@ -1,7 +1,7 @@
 """Device arithmetic on the CPU: dvi_ekf_b200/csrc/eskf_math.cuh compiled with g++ (tests/hostcheck) and
 replayed lane by lane, checked against the numpy oracle in lock-step at 1e-9 (norm-wise per state group /
 covariance block, tests/helpers.py).  Covers the first kernel's path (hc_propagate) and the building blocks of
-the warp-specialised kernel (hc_propagate2: split scalar roles, register tile, transposition)."""
+the warp-specialised kernel (hc_propagate3: split scalar roles, register tile, transposition)."""
 import ctypes
 import os
 
@@ -24,11 +24,12 @@ def hc():
     from dvi_ekf_b200 import build
 
     lib = ctypes.CDLL(build.build_hostcheck())
-    for name in ("hc_propagate", "hc_propagate2"):
+    for name in ("hc_propagate", "hc_propagate3"):
         getattr(lib, name).argtypes = [dp, dp, dp, dp, dp, ctypes.c_double, dp, dp, dp, dp]
         getattr(lib, name).restype = None
-    lib.hc_update.argtypes = [dp, dp, dp, dp, dp, dp, ctypes.c_double, dp, dp]
-    lib.hc_update.restype = ctypes.c_int
+    for name in ("hc_update", "hc_update3"):
+        getattr(lib, name).argtypes = [dp, dp, dp, dp, dp, dp, ctypes.c_double, dp, dp]
+        getattr(lib, name).restype = ctypes.c_int
     return lib
 
 
@@ -37,8 +38,8 @@ def _model(cfg):
     return np.array([cfg.length, cfg.angle, float(mask), 1.0 if cfg.zero_frozen_dofs else 0.0])
 
 
-@pytest.mark.parametrize("fn", ["hc_propagate", "hc_propagate2"])
-def test_lockstep_trajectory(hc, golden, fn):
+@pytest.mark.parametrize("fn,ufn", [("hc_propagate", "hc_update"), ("hc_propagate3", "hc_update3")])
+def test_lockstep_trajectory(hc, golden, fn, ufn):
     sc = mandala_scenario(golden, n_frames=30, ifv=10)
     kf = sc.new_oracle()
     model = _model(sc.cfg)
@@ -59,7 +60,7 @@ def test_lockstep_trajectory(hc, golden, fn):
         K = kf.update(sc.cam_meas[e, :3], sc.cam_meas[e, 3:], sc.notch_meas[e])
         cm = sc.cam_meas[e].copy()
         Kd = np.zeros((24, 7))
-        assert hc.hc_update(_p(model), _p(x), _p(P), _p(u), _p(Ro), _p(cm), sc.notch_meas[e], _p(sc.Rd), _p(Kd)) == 1
+        assert getattr(hc, ufn)(_p(model), _p(x), _p(P), _p(u), _p(Ro), _p(cm), sc.notch_meas[e], _p(sc.Rd), _p(Kd)) == 1
         xr, Pr, _, _ = kf.get_vectors()
         ws = max(ws, state_err(x, xr))
         wP = max(wP, cov_err(P, Pr, sc.Rd))
@@ -68,8 +69,8 @@ def test_lockstep_trajectory(hc, golden, fn):
 
 
 @pytest.mark.parametrize("imu_q", [False, True])
-def test_v2_blocks_equal_v1_path_on_random_states(hc, golden, imu_q):
-    """hc_propagate2 (v2 building blocks) against hc_propagate (v1 path) and the oracle on random, non-frozen
+def test_v3_blocks_equal_v1_path_on_random_states(hc, golden, imu_q):
+    """hc_propagate3 (kernel-3 building blocks) against hc_propagate (v1 path) and the oracle on random, non-frozen
     states with non-zero notch rates; with and without IMU noise in Q (Filter.py:110-117)."""
     sc = mandala_scenario(golden, n_frames=10, ifv=1, frozen_dofs=(0, 0, 0, 0, 0, 0))
     rng = np.random.default_rng(7)
@@ -88,7 +89,7 @@ def test_v2_blocks_equal_v1_path_on_random_states(hc, golden, imu_q):
         kf.propagate(dt, oa[:3], oa[3:])
         xr, Pr, ur, Rr = kf.get_vectors()
         outs = []
-        for fn in (hc.hc_propagate, hc.hc_propagate2):
+        for fn in (hc.hc_propagate, hc.hc_propagate3):
             x, P, u, Ro = x0.copy(), P0.copy(), u0.copy(), R0.copy()
             fn(_p(model), _p(x), _p(P), _p(u), _p(Ro), dt, _p(oa.copy()), _p(qd), _p(sc.sig_om), None)
             outs.append((x, P, u, Ro))
