@@ -56,7 +56,7 @@ def build_cuda(force: bool = False, verbose: bool = False, defines=(), suffix: s
     if suffix:
         OBJ = os.path.join(HERE, "build" + suffix)
         LIB = os.path.join(HERE, f"libeskf_b200{suffix}.so")
-    extra = [f"-D{d}" for d in defines]
+    extra = [f"-D{d}" for d in defines] + os.environ.get("ESKF_B200_NVCC_EXTRA", "").split()
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, h) for h in ("eskf_math.cuh", "eskf_rng.cuh", "eskf_kernel.cuh", "eskf_cov3.cuh", "eskf_kernel3.cuh")]
     headers.append(os.path.join(ROOT, "include", "eskf.h"))
@@ -110,8 +110,8 @@ def ptxas_summary() -> str:
 if __name__ == "__main__":
     for a in sys.argv[1:]:
         if a.startswith("--exp="):  # e.g. --exp=ESKF_EXP_NO_COV
-            d = a.split("=", 1)[1]
-            print(build_cuda(defines=(d,), suffix="_" + d.lower()))
+            d = a.split("=", 1)[1].split(",")  # several switches: --exp=A,B -> suffix _a_b
+            print(build_cuda(defines=tuple(d), suffix="_" + "_".join(x.lower().replace("eskf_exp_", "") for x in d)))
             sys.exit(0)
     print(build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_hostcheck())

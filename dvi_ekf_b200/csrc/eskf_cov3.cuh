@@ -19,58 +19,65 @@
 
 namespace eskf {
 
-// N consecutive coefficients starting at the (even) record offset BASE, held as pairs
-template <int PS, int BASE, int N>
+// N consecutive coefficients starting at the (even) record offset base, held as pairs
+template <int PS, int N>
 struct Coefs {
   d2 p[(N + 1) / 2];
-  ESKF_HD void load(const d2* f2) {
+  ESKF_HD void load(const d2* f2, int base) {
 #pragma unroll
-    for (int j = 0; j < (N + 1) / 2; ++j) p[j] = f2[(BASE / 2 + j) * PS];
+    for (int j = 0; j < (N + 1) / 2; ++j) p[j] = f2[(base / 2 + j) * PS];
   }
   ESKF_HD double operator()(int idx) const { return (idx & 1) ? p[idx >> 1].y : p[idx >> 1].x; }
 };
 
+// The row groups below fetch their coefficients in windows of two columns (three 16-byte pairs for a
+// three-row group): a short live range per window instead of the whole block in registers.
+
 // rows 21:24 (camera orientation error): y[i][v]
 template <int PS>
 ESKF_HD void fx3_rows_h2(const double (&X)[24][3], const d2* f2, double (&y)[3][3]) {
-  Coefs<PS, FX3_H2, 21> c;
-  c.load(f2);
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int v = 0; v < 3; ++v) y[i][v] = (i == 0) ? 0.0 : X[21 + i][v];  // Fx[22,22] = Fx[23,23] = 1
 #pragma unroll
-  for (int k = 0; k < 7; ++k) {
-    const int col = (k < 3) ? 9 + k : (k == 3) ? 15 : 19 + (k - 4);  // D on dofs 1..3 and the notch, E on 19:22 (quirk Q3)
+  for (int kb = 0; kb < 7; kb += 2) {
+    Coefs<PS, 6> c;  // columns kb, kb + 1
+    c.load(f2, FX3_H2 + 3 * kb);
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int k = kb; k < kb + 2 && k < 7; ++k) {
+      const int col = (k < 3) ? 9 + k : (k == 3) ? 15 : 19 + (k - 4);  // D on dofs 1..3 and the notch, E on 19:22 (quirk Q3)
 #pragma unroll
-      for (int v = 0; v < 3; ++v) y[i][v] += c(3 * k + i) * X[col][v];
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int v = 0; v < 3; ++v) y[i][v] += c(3 * (k - kb) + i) * X[col][v];
+    }
   }
 }
 
 // rows 18:21 (camera position error): y[i][v]
 template <int PS>
 ESKF_HD void fx3_rows_h1(const double (&X)[24][3], const d2* f2, double dt, double (&y)[3][3]) {
-  Coefs<PS, FX3_H1, 27> c;
-  c.load(f2);
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int v = 0; v < 3; ++v) y[i][v] = X[16 + i][v] + dt * X[3 + i][v];  // mis-aligned identity block (quirk Q3)
 #pragma unroll
-  for (int k = 0; k < 9; ++k)  // C1 on theta (6:9), C2 on dofs (9:15)
+  for (int kb = 0; kb < 9; kb += 2) {  // C1 on theta (6:9), C2 on dofs (9:15)
+    Coefs<PS, 6> c;
+    c.load(f2, FX3_H1 + 3 * kb);
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int k = kb; k < kb + 2 && k < 9; ++k)
 #pragma unroll
-      for (int v = 0; v < 3; ++v) y[i][v] += c(3 * k + i) * X[6 + k][v];
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int v = 0; v < 3; ++v) y[i][v] += c(3 * (k - kb) + i) * X[6 + k][v];
+  }
 }
 
 // rows 3:6  v += A theta ; rows 6:9  theta = B theta
 template <int PS>
 ESKF_HD void fx3_rows_ab(const double (&X)[24][3], const d2* f2, double (&ya)[3][3], double (&yb)[3][3]) {
-  Coefs<PS, FX3_AB, 18> c;
-  c.load(f2);
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -79,14 +86,35 @@ ESKF_HD void fx3_rows_ab(const double (&X)[24][3], const d2* f2, double (&ya)[3]
       yb[i][v] = 0.0;
     }
 #pragma unroll
-  for (int k = 0; k < 3; ++k)
+  for (int k = 0; k < 3; ++k) {
+    Coefs<PS, 6> c;
+    c.load(f2, FX3_AB + 6 * k);
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int v = 0; v < 3; ++v) {
-        ya[i][v] += c(6 * k + i) * X[6 + k][v];
-        yb[i][v] += c(6 * k + 3 + i) * X[6 + k][v];
+        ya[i][v] += c(i) * X[6 + k][v];
+        yb[i][v] += c(3 + i) * X[6 + k][v];
       }
+  }
+}
+
+// Transposed reload between the passes: X[k][v] <- T(3g+v, k) from the rows 3g..3g+2 of the buffer (row
+// stride RS doubles, 16-byte aligned), as 16-byte pairs in the order the row groups of pass 2 consume them
+// (rows 21:24 first: columns 9..11, 15, 19..23; then rows 18:21: columns 3..18; columns 0..2 last).
+template <int RS>
+ESKF_HD void fx3_load_transposed(double (&X)[24][3], const double* rows) {
+  constexpr int order[12] = {4, 5, 7, 9, 10, 11, 1, 2, 3, 6, 8, 0};
+#pragma unroll
+  for (int o = 0; o < 12; ++o) {
+    const int j = order[o];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      const d2 t = reinterpret_cast<const d2*>(rows + v * RS)[j];
+      X[2 * j][v] = t.x;
+      X[2 * j + 1][v] = t.y;
+    }
+  }
 }
 
 // Pass 1: T(:, tile) = Fx X, row i stored as out[i * OS + v] as soon as it is finished (X is not modified;
@@ -135,15 +163,18 @@ ESKF_HD void fx3_apply_store(const double (&X)[24][3], const d2* f2, double* out
 template <int PS>
 ESKF_HD void fx3_apply_inplace(double (&X)[24][3], const d2* f2) {
   const double dt = f2[(FX3_DT / 2) * PS].x;
-  double y21[3][3], y18[3][3], ya[3][3], yb[3][3];
-  fx3_rows_h2<PS>(X, f2, y21);
-  fx3_rows_h1<PS>(X, f2, dt, y18);  // reads X[18] (row 20), so rows 18:21 are assigned after it
+  double y[3][3], ya[3][3], yb[3][3];
+  fx3_rows_h2<PS>(X, f2, y);  // reads X[19..21]: before rows 18:21 change
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) X[21 + i][v] = y[i][v];
+  fx3_rows_h1<PS>(X, f2, dt, y);  // reads X[3..18]: before rows 3:9 and the notch chain change
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int v = 0; v < 3; ++v) {
-      X[21 + i][v] = y21[i][v];
-      X[18 + i][v] = y18[i][v];
+      X[18 + i][v] = y[i][v];
       X[i][v] = X[i][v] + dt * X[3 + i][v];
     }
   fx3_rows_ab<PS>(X, f2, ya, yb);
@@ -218,13 +249,22 @@ ESKF_HD void fx3_process_noise(double (&X)[24][3], int g, const d2* f2, const do
 // ---- camera update on the register tile ------------------------------------------------------------------
 // "u3 record": per-filter exchange area of the eight lanes (doubles).  Element j of the record of filter
 // q (of QS filters interleaved pair-wise) lives at rec[((j >> 1) * QS) * 2 + (j & 1)], rec already offset
-// by 2 * q: the same pair of all QS filters of a warp is one contiguous 16 * QS bytes.
+// by 2 * q: the same pair of all QS filters of a warp is one contiguous 16 * QS bytes.  The 24x7 matrices
+// are stored TRANSPOSED (7 x 24: element (m, i) at 24 m + i) so that four consecutive rows of one column m
+// are two 16-byte fetches; the passes below run column by column over blocks of four rows, twelve
+// independent accumulators at a time.
 constexpr int U3_S = 0;      // 7x7  S = H P H^T + R         (+1 pad)
 constexpr int U3_SINV = 50;  // 7x7  inv(S)                  (+1 pad)
-constexpr int U3_K = 100;    // 24x7 K
-constexpr int U3_WH = 268;   // 24x7 W(:, h_m),  W = (I - K H) P
-constexpr int U3_KR = 436;   // 24x7 K R
+constexpr int U3_K = 100;    // 7x24 K^T
+constexpr int U3_WH = 268;   // 7x24 W(:, h_m)^T,  W = (I - K H) P
+constexpr int U3_HP = 436;   // 7x24 H P: rows h_m of the prior P (each lane files the entries of its own columns)
 constexpr int U3_SIZE = 604;
+
+// The passes over the 24x7 matrices are REAL loops over the measurement index m (a few hundred instructions
+// executed seven times instead of several thousand executed once: the update runs once per camera frame and
+// straight-line code of that size is instruction-fetch bound); everything indexed by m therefore comes from
+// the record, never from a register array.
+ESKF_HD int u3_hset(int m) { return (m < 6) ? 18 + m : 15; }
 
 template <int QS>
 ESKF_HD double& u3_at(double* rec, int j) {
@@ -234,26 +274,19 @@ template <int QS>
 ESKF_HD double u3_get(const double* rec, int j) {
   return rec[((j >> 1) * QS) * 2 + (j & 1)];
 }
-// N consecutive record elements starting at element B (any parity), fetched as pairs
-template <int QS, int N>
-struct U3Row {
-  d2 p[(N + 2) / 2 + 1];
-  int b0;
-  ESKF_HD void load(const double* rec, int B) {
-    b0 = B & 1;
-    const d2* r2 = reinterpret_cast<const d2*>(rec);
-#pragma unroll
-    for (int j = 0; j < (N + 2) / 2; ++j)
-      if (2 * j < N + b0) p[j] = r2[((B >> 1) + j) * QS];
-  }
-  ESKF_HD double operator()(int i) const {
-    const int e = i + b0;
-    return (e & 1) ? p[e >> 1].y : p[e >> 1].x;
-  }
-};
+// four consecutive record elements starting at the even element j
+template <int QS>
+ESKF_HD void u3_get4(const double* rec, int j, double (&o)[4]) {
+  const d2* r2 = reinterpret_cast<const d2*>(rec);
+  const d2 a = r2[(j >> 1) * QS], b = r2[((j >> 1) + 1) * QS];
+  o[0] = a.x;
+  o[1] = a.y;
+  o[2] = b.x;
+  o[3] = b.y;
+}
 
 // owner of measurement row m: column h_m = ESKF_HSET(m) belongs to lane h_m / 3, tile column h_m % 3
-// U0a: lanes 5..7 publish their columns of S (Filter.py:355).
+// U0a: lanes 5..7 publish their columns of S (Filter.py:355); every lane files H P for its own columns.
 template <int QS>
 ESKF_HD void upd3_publish_S(const double (&X)[24][3], int g, const double* rd, double* rec) {
 #pragma unroll
@@ -263,29 +296,30 @@ ESKF_HD void upd3_publish_S(const double (&X)[24][3], int g, const double* rd, d
 #pragma unroll
       for (int i = 0; i < 7; ++i) u3_at<QS>(rec, U3_S + 7 * i + m) = X[ESKF_HSET(i)][h % 3] + ((i == m) ? rd[m] : 0.0);
     }
+#pragma unroll
+    for (int v = 0; v < 3; ++v) u3_at<QS>(rec, U3_HP + 24 * m + 3 * g + v) = X[h][v];
   }
 }
 
-// U1: gain rows 3g..3g+2  K = (P H^T) inv(S)  (Filter.py:357), published together with K R; delta = K res
-// for the same rows.
+// U1: gain rows 3g..3g+2  K = (P H^T) inv(S)  (Filter.py:357), published; delta = K res for the same rows.
 template <int QS>
-ESKF_HD void upd3_gain(const double (&X)[24][3], int g, double* rec, const double* res, const double* rd, double (&K)[3][7],
-                       double (&dl)[3]) {
-  double si[49];
-#pragma unroll
-  for (int j = 0; j < 49; ++j) si[j] = u3_get<QS>(rec, U3_SINV + j);
+ESKF_HD void upd3_gain(int g, double* rec, const double* res, double (&K)[3][7], double (&dl)[3]) {
+  // K(r, :) = sum_j P(r, h_j) inv(S)(j, :),  P(r, h_j) = P(h_j, r) = H P(j, r): everything comes from the record,
+  // the tile is not touched (the register budget of this phase is the 21 gains)
 #pragma unroll
   for (int v = 0; v < 3; ++v) {
+    double ph[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) ph[j] = u3_get<QS>(rec, U3_HP + 24 * j + 3 * g + v);
     dl[v] = 0.0;
 #pragma unroll
     for (int m = 0; m < 7; ++m) {
       double acc = 0.0;
 #pragma unroll
-      for (int j = 0; j < 7; ++j) acc += X[ESKF_HSET(j)][v] * si[7 * j + m];  // P(r, h_j) = P(h_j, r)
+      for (int j = 0; j < 7; ++j) acc += ph[j] * u3_get<QS>(rec, U3_SINV + 7 * j + m);  // (re-read per column: no 49-register copy)
       K[v][m] = acc;
       dl[v] += acc * res[m];
-      u3_at<QS>(rec, U3_K + 7 * (3 * g + v) + m) = acc;
-      u3_at<QS>(rec, U3_KR + 7 * (3 * g + v) + m) = acc * rd[m];
+      u3_at<QS>(rec, U3_K + 24 * m + 3 * g + v) = acc;
     }
   }
 }
@@ -296,32 +330,49 @@ ESKF_HD void upd3_gain(const double (&X)[24][3], int g, double* rec, const doubl
 // of the roundings is kept (tests/test_conditioning.py).
 template <int QS>
 ESKF_HD void upd3_w_pass(double (&X)[24][3], int g, double* rec) {
-  // rows outside H first (they read the still untouched rows h_m) ...
+  // rows outside H (0..14, 16, 17): column by column of K, four rows at a time, X[i][v] -= K(i, m) P(h_m, j_v)
+#pragma unroll 1
+  for (int m = 0; m < 7; ++m) {
+    double xh[3];
 #pragma unroll
-  for (int i = 0; i < 24; ++i) {
-    if (i == 15 || i >= 18) continue;
-    U3Row<QS, 7> k;
-    k.load(rec, U3_K + 7 * i);
+    for (int v = 0; v < 3; ++v) xh[v] = u3_get<QS>(rec, U3_HP + 24 * m + 3 * g + v);
 #pragma unroll
-    for (int m = 0; m < 7; ++m)
+    for (int ib = 0; ib < 12; ib += 4) {
+      double k[4];
+      u3_get4<QS>(rec, U3_K + 24 * m + ib, k);
 #pragma unroll
-      for (int v = 0; v < 3; ++v) X[i][v] -= k(m) * X[ESKF_HSET(m)][v];
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int v = 0; v < 3; ++v) X[ib + r][v] -= k[r] * xh[v];
+    }
+    double k[4], k2[4];
+    u3_get4<QS>(rec, U3_K + 24 * m + 12, k);   // rows 12..15 (15 is an H row)
+    u3_get4<QS>(rec, U3_K + 24 * m + 16, k2);  // rows 16, 17 (18, 19 are H rows)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      X[12][v] -= k[0] * xh[v];
+      X[13][v] -= k[1] * xh[v];
+      X[14][v] -= k[2] * xh[v];
+      X[16][v] -= k2[0] * xh[v];
+      X[17][v] -= k2[1] * xh[v];
+    }
   }
-  // ... then the seven rows h_a themselves
+  // the seven rows h_a themselves (they still hold the prior)
   double w[7][3];
 #pragma unroll
   for (int a = 0; a < 7; ++a) {
     const int i = ESKF_HSET(a);
-    U3Row<QS, 7> k;
-    k.load(rec, U3_K + 7 * i);
-    const double cd = 1.0 - k(a);
+    double k[7];
+#pragma unroll
+    for (int m = 0; m < 7; ++m) k[m] = u3_get<QS>(rec, U3_K + 24 * m + i);
+    const double cd = 1.0 - k[a];
 #pragma unroll
     for (int v = 0; v < 3; ++v) w[a][v] = cd * X[i][v];
 #pragma unroll
     for (int m = 0; m < 7; ++m) {
       if (m == a) continue;
 #pragma unroll
-      for (int v = 0; v < 3; ++v) w[a][v] -= k(m) * X[ESKF_HSET(m)][v];
+      for (int v = 0; v < 3; ++v) w[a][v] -= k[m] * X[ESKF_HSET(m)][v];
     }
   }
 #pragma unroll
@@ -332,60 +383,64 @@ ESKF_HD void upd3_w_pass(double (&X)[24][3], int g, double* rec) {
   for (int m = 0; m < 7; ++m) {
     const int h = ESKF_HSET(m);
     if (g == h / 3) {
+      d2* r2 = reinterpret_cast<d2*>(rec);
 #pragma unroll
-      for (int i = 0; i < 24; ++i) u3_at<QS>(rec, U3_WH + 7 * i + m) = X[i][h % 3];
+      for (int i = 0; i < 24; i += 2) r2[((U3_WH + 24 * m + i) >> 1) * QS] = d2{X[i][h % 3], X[i + 1][h % 3]};
     }
   }
 }
 
-// U2b: X <- W (I - K H)^T for the tile columns j = 3g+v:  W(:,j) (1 - K[j][a]) - sum_{m != a} W(:,h_m) K[j][m]
+// U2b: X <- W (I - K H)^T + (K R) K^T for the tile columns j = 3g+v  (Filter.py:384):
+//   W(:,j) (1 - K[j][a]) - sum_{m != a} W(:,h_m) K[j][m] + sum_m K(:,m) (R_m K[j][m])
+// then the reset P <- G P G^T with G = I - [delta_theta / 2]x on 6:9 and 21:24 (Filter.py:386-390).
 template <int QS>
-ESKF_HD void upd3_finish_a(double (&X)[24][3], int g, const double* rec) {
-  double Kz[3][7], cdv[3];
+ESKF_HD void upd3_finish(double (&X)[24][3], int g, const double* rec, const double* rd, const double* dth,
+                         const double* dthc) {
+  // (1 - K[j][a]) for a column j = h_a measured directly, 1 otherwise: lanes 5 (column 15), 6 and 7
+  double cdv[3];
 #pragma unroll
   for (int v = 0; v < 3; ++v) {
-    cdv[v] = 1.0;
-#pragma unroll
-    for (int m = 0; m < 7; ++m) {
-      const double k = u3_get<QS>(rec, U3_K + 7 * (3 * g + v) + m);
-      const bool diag = (ESKF_HSET(m) == 3 * g + v);
-      Kz[v][m] = diag ? 0.0 : k;
-      if (diag) cdv[v] = 1.0 - k;
-    }
+    const int j = 3 * g + v;
+    const int a = (j >= 18) ? j - 18 : 6;  // only used when j is in H
+    const double k = u3_get<QS>(rec, U3_K + 24 * a + j);
+    cdv[v] = (j >= 18 || j == 15) ? 1.0 - k : 1.0;
   }
 #pragma unroll
-  for (int i = 0; i < 24; ++i) {
-    U3Row<QS, 7> wh;
-    wh.load(rec, U3_WH + 7 * i);
+  for (int i = 0; i < 24; ++i)
 #pragma unroll
     for (int v = 0; v < 3; ++v) X[i][v] = cdv[v] * X[i][v];
+#pragma unroll 1
+  for (int m = 0; m < 7; ++m) {
+    double kz[3];
 #pragma unroll
-    for (int m = 0; m < 7; ++m)
+    for (int v = 0; v < 3; ++v) {
+      const double k = u3_get<QS>(rec, U3_K + 24 * m + 3 * g + v);
+      kz[v] = (u3_hset(m) == 3 * g + v) ? 0.0 : k;
+    }
 #pragma unroll
-      for (int v = 0; v < 3; ++v) X[i][v] -= wh(m) * Kz[v][m];
+    for (int ib = 0; ib < 24; ib += 4) {
+      double wh[4];
+      u3_get4<QS>(rec, U3_WH + 24 * m + ib, wh);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int v = 0; v < 3; ++v) X[ib + r][v] -= wh[r] * kz[v];
+    }
   }
-}
-
-// U2c: X += (K R) K(tile rows)^T  (Filter.py:384), then the reset P <- G P G^T with
-// G = I - [delta_theta / 2]x on 6:9 and 21:24 (Filter.py:386-390).
-template <int QS>
-ESKF_HD void upd3_finish_b(double (&X)[24][3], int g, const double* rec, const double* dth, const double* dthc) {
-  double K[3][7];
+#pragma unroll 1
+  for (int m = 0; m < 7; ++m) {
+    double kjr[3];
 #pragma unroll
-  for (int v = 0; v < 3; ++v)
+    for (int v = 0; v < 3; ++v) kjr[v] = rd[m] * u3_get<QS>(rec, U3_K + 24 * m + 3 * g + v);
 #pragma unroll
-    for (int m = 0; m < 7; ++m) K[v][m] = u3_get<QS>(rec, U3_K + 7 * (3 * g + v) + m);
+    for (int ib = 0; ib < 24; ib += 4) {
+      double k[4];
+      u3_get4<QS>(rec, U3_K + 24 * m + ib, k);
 #pragma unroll
-  for (int i = 0; i < 24; ++i) {
-    U3Row<QS, 7> kr;
-    kr.load(rec, U3_KR + 7 * i);
-    double z[3] = {0.0, 0.0, 0.0};
+      for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int m = 0; m < 7; ++m)
-#pragma unroll
-      for (int v = 0; v < 3; ++v) z[v] += kr(m) * K[v][m];
-#pragma unroll
-    for (int v = 0; v < 3; ++v) X[i][v] += z[v];
+        for (int v = 0; v < 3; ++v) X[ib + r][v] += k[r] * kjr[v];
+    }
   }
   const double gt[3] = {0.5 * dth[0], 0.5 * dth[1], 0.5 * dth[2]};
   const double gc[3] = {0.5 * dthc[0], 0.5 * dthc[1], 0.5 * dthc[2]};

@@ -19,8 +19,12 @@
 //                   memory (72 STS.64 + 36 LDS.128 per lane); the camera update (gain, Joseph form,
 //                   reset) works on the same register tile and exchanges only S, K, K R, W(:,h) (7-wide
 //                   records) between the eight lanes of a filter, with warp-level synchronisation.
-// The scalar roles of step k run concurrently with the covariance role of step k-1; all roles meet at one
-// CTA barrier per step.  Records exchanged through shared memory are double buffered:
+// Inside an epoch (the IMU steps between two camera frames) the scalar roles and the covariance warps are
+// decoupled: the scalar roles synchronise among themselves (named barrier, 128 threads) and hand the Jacobian
+// record of a step to the covariance warps through a two-slot full / empty mbarrier pipeline, so they run up
+// to two steps ahead and every covariance warp free-runs at its own pace (their shared-memory and FP64 phases
+// drift apart instead of colliding at a CTA barrier per step).  All roles meet at CTA barriers only around
+// the camera update.  Records exchanged through shared memory are double buffered:
 //   RING[4]  samples (slot (k+1)&3 = new sample of step k, slot k&3 = old sample)       STAGER -> IMU, CAMERA, JACOB
 //   RO/RW/V[2] R_WB_old, R_WB and v at the start of step k (slot k&1)                   IMU -> CAMERA, JACOB
 //   PK[2]    probe kinematics + notch, notch' at the start of step k (slot k&1)         JACOB -> CAMERA
@@ -71,7 +75,8 @@ struct Lay3 {
   static constexpr int TB = 0;                  // [F][TB3_STRIDE]  (u3 records of a warp's four filters during the update)
   static constexpr int SX = F * TB3_STRIDE;     // [SX3_SIZE][F]
   static constexpr int FXB = SX + SX3_SIZE * F; // [2][FX3_NPAIR][F] d2
-  static constexpr int TOTAL = FXB + 2 * FX3_NPAIR * 2 * F;  // doubles
+  static constexpr int MBAR = FXB + 2 * FX3_NPAIR * 2 * F;   // 4 mbarriers: full[2], empty[2]
+  static constexpr int TOTAL = MBAR + 4;                     // doubles
   static_assert((SX % 2) == 0 && (FXB % 2) == 0, "16-byte alignment");
   static_assert(4 * U3_SIZE <= 4 * TB3_STRIDE, "update records must fit the transposition buffers of a warp");
 };
@@ -85,6 +90,61 @@ __device__ __forceinline__ void reg_dec3() {
   if constexpr (N > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(N));
 }
 
+// ---- mbarrier pipeline of the Jacobian records (producers: IMU + JACOB warps, consumers: covariance warps) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// one arrival for the whole warp: its lanes' shared-memory traffic is ordered by __syncwarp, lane 0 releases it
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0)
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// the same for a warp that is AHEAD of its partner (producers waiting for a free slot): back off between polls
+// so that the polling does not take issue slots from the covariance warps of the sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
+}
+// step kk uses record slot kk & 1; its full barrier completes phase kk >> 1, and the slot is free for step kk
+// once the consumers of step kk - 2 have arrived on its empty barrier (phase (kk - 2) >> 1)
+__device__ __forceinline__ void fx_slot_acquire(uint64_t* mbar, int64_t kk) {  // producers, before writing
+  if (kk >= 2) mbar_wait_relaxed(mbar + 2 + (kk & 1), (uint32_t)(((kk - 2) >> 1) & 1));
+}
+__device__ __forceinline__ void fx_slot_publish(uint64_t* mbar, int64_t kk) { mbar_arrive_warp(mbar + (kk & 1)); }
+__device__ __forceinline__ void fx_slot_wait(uint64_t* mbar, int64_t kk) {  // consumers, before reading
+  mbar_wait(mbar + (kk & 1), (uint32_t)((kk >> 1) & 1));
+}
+__device__ __forceinline__ void fx_slot_release(uint64_t* mbar, int64_t kk) { mbar_arrive_warp(mbar + 2 + (kk & 1)); }
+// barrier of the four scalar-role warps
+__device__ __forceinline__ void scalar_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 struct Ctx3 {
   double* smem;
   int64_t f0;      // first local filter of the CTA
@@ -93,6 +153,7 @@ struct Ctx3 {
   int64_t traj;
   const int32_t* n_prop;
   const double* dtp;
+  uint64_t* mbar;  // full[2], empty[2]
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -179,9 +240,10 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
   int64_t k = 0;
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
-    for (int it = 0; it <= n; ++it) {
-      if (act && it < n && ESKF3_SCALAR_ON(it)) {
-        const int64_t kk = k + it;
+    for (int it = 0; it < n; ++it) {
+      const int64_t kk = k + it;
+      fx_slot_acquire(c.mbar, kk);  // the covariance warps are done with the record of step kk - 2
+      if (act && ESKF3_SCALAR_ON(it)) {
         const double* uo = sx + (SX3_RING + 8 * (int)(kk & 3)) * F;
         const double* un = sx + (SX3_RING + 8 * (int)((kk + 1) & 3)) * F;
         double om_old[3], acc_old[3], om[3], acc[3];
@@ -196,7 +258,7 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
         {  // rows 3:9 of Fx (Filter.py:253-255) from the buffered R_WB_old / om_old / acc_old: this role has them
           double fx[FX3_SIZE];
           jac_rows_ab(Rold, dt, om_old, acc_old, fx);
-          d2* dst = fxb + ((it & 1) * FX3_NPAIR) * F;
+          d2* dst = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
 #pragma unroll
           for (int j = FX3_AB / 2; j < FX3_MAIN / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
         }
@@ -211,10 +273,12 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
 #pragma unroll
         for (int i = 0; i < 3; ++i) sx[(SX3_V + 3 * s + i) * F] = v[i];
       }
-      __syncthreads();
+      fx_slot_publish(c.mbar, kk);  // rows 3:9 of the record of step kk are in place
+      scalar_barrier();
     }
     k += n;
     if (!a.do_update) continue;
+    scalar_barrier();  // (an update-only launch has no step barrier: the measurement must be staged before U0)
     __syncthreads();  // U0 | U1
     __syncthreads();  // U1 | U2
     if (act) {
@@ -299,8 +363,8 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
   int64_t k = 0;
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
-    for (int it = 0; it <= n; ++it) {
-      if (act && it < n && ESKF3_SCALAR_ON(it)) {
+    for (int it = 0; it < n; ++it) {
+      if (act && ESKF3_SCALAR_ON(it)) {
         const int64_t kk = k + it;
         const double* uo = sx + (SX3_RING + 8 * (int)(kk & 3)) * F;
         const double* un = sx + (SX3_RING + 8 * (int)((kk + 1) & 3)) * F;
@@ -323,10 +387,11 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
         const double notch_d = sx[(SX3_PK + 17 * s + 16) * F];
         cam_nominal_step(pc, qc, vpre, Rwb, dt, om_old, om, pkp, pkR, pkz, notch_d);
       }
-      __syncthreads();
+      scalar_barrier();
     }
     k += n;
     if (!a.do_update) continue;
+    scalar_barrier();  // (an update-only launch has no step barrier: the measurement must be staged before U0)
     // ---- U0: residual (Filter.py:363-375) ----
     if (lane < F) {
       bool ok = false;
@@ -434,9 +499,10 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
   int64_t k = 0;
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
-    for (int it = 0; it <= n; ++it) {
-      if (act && it < n && ESKF3_SCALAR_ON(it)) {
-        const int64_t kk = k + it;
+    for (int it = 0; it < n; ++it) {
+      const int64_t kk = k + it;
+      fx_slot_acquire(c.mbar, kk);  // the covariance warps are done with the record of step kk - 2
+      if (act && ESKF3_SCALAR_ON(it)) {
         const double* uo = sx + (SX3_RING + 8 * (int)(kk & 3)) * F;
         const double dt = sx[(SX3_RING + 8 * (int)((kk + 1) & 3) + 6) * F];
         const int s = (int)(kk & 1), sn = s ^ 1;
@@ -455,7 +521,7 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
         for (int i = 0; i < 3; ++i) om_old[i] = uo[i * F];
 #pragma unroll
         for (int i = 0; i < 9; ++i) Ro[i] = sx[(SX3_RO + 9 * s + i) * F];
-        d2* dst = fxb + ((it & 1) * FX3_NPAIR) * F;
+        d2* dst = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
         double fx[FX3_SIZE];
         // every row group is shipped as soon as it is final (short register live ranges)
         jac_rows_h2(a.model, notch[1], pk, trv, dt, om_old, sig_om, fx);
@@ -470,10 +536,12 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
           for (int j = FX3_NPAIR_MAIN; j < FX3_NPAIR; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
         }
       }
-      __syncthreads();
+      fx_slot_publish(c.mbar, kk);  // dt, rows 18:24 (and the noise rows) of the record of step kk are in place
+      scalar_barrier();
     }
     k += n;
     if (!a.do_update) continue;
+    scalar_barrier();  // (an update-only launch has no step barrier: the measurement must be staged before U0)
     __syncthreads();  // U0 | U1
     __syncthreads();  // U1 | U2
     if (act) {
@@ -570,15 +638,14 @@ __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int l
   int64_t k = 0;
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
-    for (int it = 0; it <= n; ++it) {
-      if (act) {
-        if (it == 0 && a.do_update) stage_meas(e);
-        if (it < n && k + it + 1 < a.T && ESKF3_SCALAR_ON(it)) stage_sample(k + it + 1);
-      }
-      __syncthreads();
+    if (act && a.do_update) stage_meas(e);
+    for (int it = 0; it < n; ++it) {
+      if (act && k + it + 1 < a.T && ESKF3_SCALAR_ON(it)) stage_sample(k + it + 1);
+      scalar_barrier();
     }
     k += n;
     if (!a.do_update) continue;
+    scalar_barrier();  // (an update-only launch has no step barrier: the measurement must be staged before U0)
     __syncthreads();  // U0 | U1
     __syncthreads();  // U1 | U2
     __syncthreads();  // U2 done
@@ -589,6 +656,19 @@ __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int l
 
 // ---------------------------------------------------------------------------------------------
 // covariance role
+
+// 1 / x without the special-case subroutine of the compiler's division (SFU seed + three Newton steps, <= 1 ulp;
+// zero / non-finite input gives a non-finite result, which the caller detects)
+__device__ __forceinline__ double rcp_nr(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+  }
+  return r;
+}
 
 // inv(S) by the eight lanes of a filter: lane c < 7 owns column c of [S | I].  LU with partial pivoting
 // + back substitution, the same operations in the same order as eskf::inv7 (the host-checkable
@@ -606,6 +686,7 @@ __device__ __forceinline__ bool inv7_group3(double* rec, int g) {
     b[i] = (i == c) ? 1.0 : 0.0;
   }
   bool ok = true;
+  double rpiv = 0.0;
 #pragma unroll
   for (int k = 0; k < 7; ++k) {
     int piv = k;
@@ -632,7 +713,8 @@ __device__ __forceinline__ bool inv7_group3(double* rec, int g) {
         b[i] = t;
       }
     }
-    const double rp = 1.0 / a[k];
+    const double rp = rcp_nr(a[k]);
+    if (k == c) rpiv = rp;  // 1 / U(k, k), needed again by the back substitution
 #pragma unroll
     for (int i = k + 1; i < 7; ++i) {
       const double l = __shfl_sync(FULL, a[i] * rp, k, 8);
@@ -648,8 +730,7 @@ __device__ __forceinline__ bool inv7_group3(double* rec, int g) {
       const double uik = __shfl_sync(FULL, a[i], k, 8);
       v -= uik * b[k];
     }
-    const double uii = __shfl_sync(FULL, a[i], i, 8);
-    b[i] = v * (1.0 / uii);
+    b[i] = v * __shfl_sync(FULL, rpiv, i, 8);
   }
   double chk = 0.0;
 #pragma unroll
@@ -708,24 +789,43 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
   load_rows();
   __syncthreads();  // prologue
 
+  int64_t k = 0;
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
-    for (int it = 0; it <= n; ++it) {
-      if (it >= 1 && ESKF3_COV_ON) {
-        const d2* f2 = fxb + (((it - 1) & 1) * FX3_NPAIR) * F;
+    for (int it = 0; it < n; ++it) {
+      const int64_t kk = k + it;
+      fx_slot_wait(c.mbar, kk);  // the Jacobian record of step kk is complete
+      if (ESKF3_COV_ON) {
+        const d2* f2 = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
         // pass 1: T(:, 3g..3g+2) = Fx P(:, 3g..3g+2), rows stored as they are finished
+#ifndef ESKF_EXP_NO_TRANSPOSE
         fx3_apply_store<F, RS3>(X, f2, Tb + 3 * cg);
         __syncwarp(gmask);
         load_rows();  // X[k][v] = T(3g+v, k)
         __syncwarp(gmask);
+#else  // (profiling experiment: the arithmetic of pass 1 without the shared-memory transposition; wrong results)
+        fx3_apply_inplace<F>(X, f2);
+#endif
         // pass 2: P'(3g+v, :) = Fx T(3g+v, :)^T
         fx3_apply_inplace<F>(X, f2);
-        fx3_process_noise<F>(X, cg, f2, qdv, qd, imu_q);
+        // (the lane index is laundered through an empty asm so that the thirteen selected addends of the diagonal
+        // are formed here, two selects each, instead of being hoisted out of the loop and spilled)
+        int gl = cg;
+        asm volatile("" : "+r"(gl));
+        fx3_process_noise<F>(X, gl, f2, qdv, qd, imu_q);
       }
-      __syncthreads();
+      fx_slot_release(c.mbar, kk);  // this warp is done with the record
     }
+    k += n;
     if (!a.do_update) continue;
     // ---- U0: S and its inverse (the scalar CAMERA role computes the residual meanwhile) ----
+#ifdef ESKF_EXP_NO_UPDATE  // (profiling experiment: propagation only)
+    __syncthreads();
+    if (cg == 0) sxw[SX3_OK2 * F] = 0.0;
+    __syncthreads();
+    __syncthreads();
+    continue;
+#endif
     double rd[7];
 #pragma unroll
     for (int m = 0; m < 7; ++m) rd[m] = sxc[(SX3_RD + m) * F];
@@ -738,7 +838,7 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
       double K[3][7], res[7], dl[3];
 #pragma unroll
       for (int m = 0; m < 7; ++m) res[m] = sxc[(SX3_RES + m) * F];
-      upd3_gain<4>(X, cg, rec, res, rd, K, dl);
+      upd3_gain<4>(cg, rec, res, K, dl);
 #pragma unroll
       for (int v = 0; v < 3; ++v) sxw[(SX3_DELTA + 3 * cg + v) * F] = dl[v];
       if (a.K_out && cf < c.nf) {
@@ -753,10 +853,9 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
     if (upd_c) {
       upd3_w_pass<4>(X, cg, rec);
       __syncwarp(gmask);
-      upd3_finish_a<4>(X, cg, rec);
       const double dth[3] = {sxc[(SX3_DELTA + 6) * F], sxc[(SX3_DELTA + 7) * F], sxc[(SX3_DELTA + 8) * F]};
       const double dthc[3] = {sxc[(SX3_DELTA + 21) * F], sxc[(SX3_DELTA + 22) * F], sxc[(SX3_DELTA + 23) * F]};
-      upd3_finish_b<4>(X, cg, rec, dth, dthc);
+      upd3_finish<4>(X, cg, rec, rd, dth, dthc);
     }
     __syncthreads();  // U2 done
   }
@@ -780,6 +879,13 @@ __global__ void __launch_bounds__(128 + 8 * F, 1) eskf_kernel3(const __grid_cons
   c.traj = (a.n_traj > 1) ? (c.gid0 / a.filters_per_traj) : 0;
   c.n_prop = a.n_prop ? a.n_prop + c.traj * a.E : nullptr;
   c.dtp = a.dt ? a.dt + c.traj * a.T : nullptr;
+  c.mbar = reinterpret_cast<uint64_t*>(smem + L::MBAR);
+  if (tid == 0) {
+    mbar_init(c.mbar + 0, 2);      // full[s]:  the IMU and the JACOB warp
+    mbar_init(c.mbar + 1, 2);
+    mbar_init(c.mbar + 2, F / 4);  // empty[s]: the covariance warps
+    mbar_init(c.mbar + 3, F / 4);
+  }
 
   // ---- covariance tiles and parameters (coalesced) ----
   for (int idx = tid; idx < F * 576; idx += NTHR) {

@@ -1,0 +1,7 @@
+# A/B timing of alternative builds of the library: bash tools/gpu_ab.sh <suffix> [<suffix> ...]   ("" = product build)
+mkdir -p gpurun_out
+for sfx in "$@"; do
+  lib=$PWD/dvi_ekf_b200/libeskf_b200$sfx.so
+  echo "== $lib"
+  ESKF_B200_LIB=$lib timeout 150 python tools/variant_bench.py --variants 3 --n 4096 --reps 3 2>&1 | tee gpurun_out/ab$sfx.log
+done
