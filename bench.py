@@ -119,7 +119,7 @@ def run_reference_arm(a):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    fpp, n_epochs = 256, 8  # bounded sample: cores x 256 filters x 8 epochs (80 propagates + 8 updates)
+    fpp, n_epochs = 256, 32  # bounded sample per step: cores x 256 filters x 32 epochs (320 propagates + 32 updates)
     for _ in range(a.warmup):
         cpu_sample(cores, 32, 1)
     times, work = [], 0
@@ -161,7 +161,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -228,7 +228,7 @@ def run_ours(a):
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        fpp, n_ep = 256, 8
+        fpp, n_ep = 512, E  # bounded sample: 512 filters per core over the whole trajectory (10-30 s of CPU work)
         work, busy, wall = cpu_sample(cores, fpp, n_ep)
         cpu = {"value": work / busy, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{cores} procs x {fpp} filters x {n_ep} epochs of the same trajectory "
@@ -377,7 +377,7 @@ def run_ours(a):
             "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (ms * 1e-3) * 1e-9,
                     "peak_gbs": peaks.get("hbm_gbs"), "peak_source": which + " (MEASURED_PEAKS.json)"},
             "traffic": (tr or {}).get("dram_bytes_per_launch"),
-            "kernel": "eskf::eskf_kernel<F> (one launch per pass)",
+            "kernel": "eskf::eskf_kernel3<F> (one launch per pass)",
         }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),

@@ -19,7 +19,7 @@ NSTAT = 16
 EXPORTS = (
     "eskf_create", "eskf_destroy", "eskf_set_state", "eskf_set_noise", "eskf_propagate", "eskf_update",
     "eskf_run", "eskf_get_state", "eskf_sync", "eskf_launch_count", "eskf_set_tuning", "eskf_last_error",
-    "eskf_version", "eskf_fp64_peak", "eskf_set_variant",
+    "eskf_version", "eskf_fp64_peak", "eskf_set_variant", "eskf_noise_dump",
 )
 
 
@@ -89,6 +89,7 @@ def load():
     lib.eskf_set_tuning.argtypes = [vp, i32]
     lib.eskf_set_variant.argtypes = [vp, i32]
     lib.eskf_fp64_peak.argtypes = [i32, vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.eskf_noise_dump.argtypes = [i32, vp, C.c_uint64, i64, i64, i64, i64, i32, vp, i32]
     lib.eskf_last_error.restype = C.c_char_p
     lib.eskf_version.restype = C.c_char_p
     for name in EXPORTS:

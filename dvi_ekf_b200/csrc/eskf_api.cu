@@ -67,6 +67,17 @@ __global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
   if (s == 123.456) out[0] = s;  // keeps the chain alive without a store in the common case
 }
 
+// eskf_noise_dump: the standard normals of (filter, step, kind), exactly as the persistent kernels draw them
+__global__ void noise_dump_kernel(double* out, uint64_t seed, int64_t filter_id0, int64_t n_filters, int64_t step0, int64_t n_steps,
+                                  uint32_t kind) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_filters * n_steps) return;
+  const int64_t f = i / n_steps, k = i - f * n_steps;
+  double z[8];
+  normal8(seed, (uint64_t)(filter_id0 + f), (uint64_t)(step0 + k), kind, z);
+  for (int j = 0; j < 8; ++j) out[i * 8 + j] = z[j];
+}
+
 thread_local std::string g_err;
 
 }  // namespace
@@ -208,7 +219,7 @@ static void base_args(const eskf_t* h, KArgs& a) {
 extern "C" {
 
 const char* eskf_last_error(void) { return g_err.c_str(); }
-const char* eskf_version(void) { return "eskf_b200 0.2 (sm_100a)"; }
+const char* eskf_version(void) { return "eskf_b200 0.3 (sm_100a)"; }
 
 int eskf_create(const eskf_model_t* model, int64_t n_filters, int device, void* cuda_stream, eskf_t** out) {
   if (!model || !out || n_filters <= 0) {
@@ -513,6 +524,28 @@ int eskf_fp64_peak(int device, void* cuda_stream, int repeats, double* tflops_ou
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(d);
+  return ESKF_OK;
+}
+
+int eskf_noise_dump(int device, void* cuda_stream, uint64_t seed, int64_t filter_id0, int64_t n_filters, int64_t step0,
+                    int64_t n_steps, int kind, double* out, int mem) {
+  if (!out || n_filters <= 0 || n_steps <= 0 || (kind != (int)RNG_KIND_IMU && kind != (int)RNG_KIND_CAM)) {
+    g_err = "eskf_noise_dump: bad argument";
+    return ESKF_EINVAL;
+  }
+  CK(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int64_t tot = n_filters * n_steps;
+  const size_t bytes = (size_t)tot * 8 * sizeof(double);
+  double* d = out;
+  if (mem == ESKF_MEM_HOST) CK(cudaMalloc(&d, bytes));
+  noise_dump_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(d, seed, filter_id0, n_filters, step0, n_steps, (uint32_t)kind);
+  CK(cudaGetLastError());
+  if (mem == ESKF_MEM_HOST) {
+    CK(cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFree(d));
+  }
   return ESKF_OK;
 }
 

@@ -12,8 +12,8 @@
 #endif
 #ifndef ESKF_REG_S
 #if ESKF_F > 16
-#define ESKF_REG_S 120
-#define ESKF_REG_C 192
+#define ESKF_REG_S 104
+#define ESKF_REG_C 200
 #else
 #define ESKF_REG_S 0
 #define ESKF_REG_C 0

@@ -239,8 +239,20 @@ class BatchFilter:
         check(self._lib.eskf_set_tuning(self._h, int(filters_per_cta)), "eskf_set_tuning")
 
     def set_variant(self, variant: int = 0):
-        """0 = default kernel (warp-specialised v2), 1 = first kernel (v1), 2 = v2."""
+        """0 = default kernel (warp-specialised eskf_kernel3), 1 = first kernel (eskf_kernel), 3 = eskf_kernel3."""
         check(self._lib.eskf_set_variant(self._h, int(variant)), "eskf_set_variant")
+
+
+NOISE_IMU, NOISE_CAM = 1, 2
+
+
+def noise_samples(seed: int, filter_id0: int, n_filters: int, step0: int, n_steps: int, kind: int, device: int = 0):
+    """The standard normals ``eskf_run`` draws (see include/eskf.h, eskf_noise_dump): array [n_filters, n_steps, 8]."""
+    lib = _lib.load()
+    out = np.empty((n_filters, n_steps, 8))
+    check(lib.eskf_noise_dump(int(device), None, int(seed), int(filter_id0), int(n_filters), int(step0), int(n_steps), int(kind),
+                              out.ctypes.data_as(C.c_void_p), MEM_HOST), "eskf_noise_dump")
+    return out
 
 
 def fp64_peak_tflops(device: int = 0, repeats: int = 5) -> float:

@@ -73,7 +73,8 @@ typedef struct {
   const double* imu_ref;    /* [n_traj,E,6] IMU ref vx vy vz rx ry rz(deg)  (Filter.py:408-413) */
   double gt_dofs[6];        /* config.gt_imu_dofs (Filter.py:452-455) */
   /* Monte-Carlo extension (the reference is noise free): zero-mean Gaussian noise drawn
-   * in-kernel from Philox4x32-10(key = seed, counter = (step, kind, filter id)) */
+   * in-kernel from Philox4x32-10(key = seed, counter = (step, kind, filter id)), single-precision
+   * Box-Muller on the SFU; the samples of a run can be read back with eskf_noise_dump() */
   uint64_t seed;
   int64_t filter_id0;       /* global id of this handle's first filter (multi-GPU sharding) */
   double imu_noise_std[6];  /* added to om(3), acc(3) of every IMU sample */
@@ -124,9 +125,19 @@ int eskf_sync(eskf_t* h);
 int64_t eskf_launch_count(const eskf_t* h);
 /* filters per CTA used for the kernels (tunable; 0 = automatic) */
 int eskf_set_tuning(eskf_t* h, int filters_per_cta);
-/* kernel variant: 0 = default (the warp-specialised eskf_kernel2), 1 = eskf_kernel (first version, kept for
- * A/B measurements), 2 = eskf_kernel2 */
+/* kernel variant: 0 = default (the warp-specialised eskf_kernel3), 1 = eskf_kernel (first version, kept for
+ * A/B measurements), 3 = eskf_kernel3 */
 int eskf_set_variant(eskf_t* h, int variant);
+
+/* Monte-Carlo noise read-back (no reference counterpart): the standard normals the kernels draw for
+ * filters filter_id0 .. filter_id0 + n_filters - 1 and steps step0 .. step0 + n_steps - 1 of one stream,
+ * out[n_filters][n_steps][8].  kind = ESKF_NOISE_IMU: z[0..5] scale om(3), acc(3) of IMU sample `step`;
+ * kind = ESKF_NOISE_CAM: z[0..2] camera position, z[3..5] small body rotation of the measured quaternion,
+ * z[6] notch angle of camera epoch `step`.  The generator uses the device's SFU approximations, so THIS is
+ * the definition of the noise a run saw: parity tests feed these samples to the oracle. */
+enum { ESKF_NOISE_IMU = 1, ESKF_NOISE_CAM = 2 };
+int eskf_noise_dump(int device, void* cuda_stream, uint64_t seed, int64_t filter_id0, int64_t n_filters, int64_t step0,
+                    int64_t n_steps, int kind, double* out, int mem);
 
 /* Measurement aid (no reference counterpart): sustained FP64 FMA throughput of the device in
  * TFLOP/s (best of `repeats` launches of a pure DFMA kernel) -- the roofline denominator. */
