@@ -305,21 +305,35 @@ ESKF_HD void upd3_publish_S(const double (&X)[24][3], int g, const double* rd, d
 template <int QS>
 ESKF_HD void upd3_gain(int g, double* rec, const double* res, double (&K)[3][7], double (&dl)[3]) {
   // K(r, :) = sum_j P(r, h_j) inv(S)(j, :),  P(r, h_j) = P(h_j, r) = H P(j, r): everything comes from the record,
-  // the tile is not touched (the register budget of this phase is the 21 gains)
+  // the tile is not touched.  Two sweeps over the rows of inv(S) (columns 0..3, then 4..6): twelve / nine
+  // independent accumulators each.
+#pragma unroll
+  for (int v = 0; v < 3; ++v)
+#pragma unroll
+    for (int m = 0; m < 7; ++m) K[v][m] = 0.0;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int m0 = half ? 4 : 0, m1 = half ? 7 : 4;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      double ph[3], si[4];
+#pragma unroll
+      for (int v = 0; v < 3; ++v) ph[v] = u3_get<QS>(rec, U3_HP + 24 * j + 3 * g + v);
+#pragma unroll
+      for (int m = m0; m < m1; ++m) si[m - m0] = u3_get<QS>(rec, U3_SINV + 7 * j + m);
+#pragma unroll
+      for (int v = 0; v < 3; ++v)
+#pragma unroll
+        for (int m = m0; m < m1; ++m) K[v][m] += ph[v] * si[m - m0];
+    }
+  }
 #pragma unroll
   for (int v = 0; v < 3; ++v) {
-    double ph[7];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) ph[j] = u3_get<QS>(rec, U3_HP + 24 * j + 3 * g + v);
     dl[v] = 0.0;
 #pragma unroll
     for (int m = 0; m < 7; ++m) {
-      double acc = 0.0;
-#pragma unroll
-      for (int j = 0; j < 7; ++j) acc += ph[j] * u3_get<QS>(rec, U3_SINV + 7 * j + m);  // (re-read per column: no 49-register copy)
-      K[v][m] = acc;
-      dl[v] += acc * res[m];
-      u3_at<QS>(rec, U3_K + 24 * m + 3 * g + v) = acc;
+      dl[v] += K[v][m] * res[m];
+      u3_at<QS>(rec, U3_K + 24 * m + 3 * g + v) = K[v][m];
     }
   }
 }
@@ -393,7 +407,8 @@ ESKF_HD void upd3_w_pass(double (&X)[24][3], int g, double* rec) {
 // U2b: X <- W (I - K H)^T + (K R) K^T for the tile columns j = 3g+v  (Filter.py:384):
 //   W(:,j) (1 - K[j][a]) - sum_{m != a} W(:,h_m) K[j][m] + sum_m K(:,m) (R_m K[j][m])
 // then the reset P <- G P G^T with G = I - [delta_theta / 2]x on 6:9 and 21:24 (Filter.py:386-390).
-template <int QS>
+//   rd[m * RDS] = diag(R)[m]: read from memory inside the loop over m (a register array cannot be indexed by m)
+template <int QS, int RDS>
 ESKF_HD void upd3_finish(double (&X)[24][3], int g, const double* rec, const double* rd, const double* dth,
                          const double* dthc) {
   // (1 - K[j][a]) for a column j = h_a measured directly, 1 otherwise: lanes 5 (column 15), 6 and 7
@@ -431,7 +446,7 @@ ESKF_HD void upd3_finish(double (&X)[24][3], int g, const double* rec, const dou
   for (int m = 0; m < 7; ++m) {
     double kjr[3];
 #pragma unroll
-    for (int v = 0; v < 3; ++v) kjr[v] = rd[m] * u3_get<QS>(rec, U3_K + 24 * m + 3 * g + v);
+    for (int v = 0; v < 3; ++v) kjr[v] = rd[m * RDS] * u3_get<QS>(rec, U3_K + 24 * m + 3 * g + v);
 #pragma unroll
     for (int ib = 0; ib < 24; ib += 4) {
       double k[4];

@@ -316,7 +316,7 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
         mse_sum += acc2;
       }
     }
-    __syncthreads();  // U2 done
+    scalar_barrier();  // U2 of the scalar roles done (the covariance warps do not wait: see role3_cov)
   }
   // ---- write back ----
   if (act) {
@@ -446,7 +446,7 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
         mse_sum += acc2;
       }
     }
-    __syncthreads();  // U2 done
+    scalar_barrier();  // U2 of the scalar roles done (the covariance warps do not wait: see role3_cov)
   }
   if (act) {
     double* xg = a.x + (c.f0 + lane) * NX;
@@ -557,7 +557,7 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
         put_notch((int)(k & 1), notch);
       }
     }
-    __syncthreads();  // U2 done
+    scalar_barrier();  // U2 of the scalar roles done (the covariance warps do not wait: see role3_cov)
   }
   if (act) {
     double* xg = a.x + (c.f0 + lane) * NX;
@@ -650,7 +650,7 @@ __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int l
     scalar_barrier();  // (an update-only launch has no step barrier: the measurement must be staged before U0)
     __syncthreads();  // U0 | U1
     __syncthreads();  // U1 | U2
-    __syncthreads();  // U2 done
+    scalar_barrier();  // U2 of the scalar roles done (the covariance warps do not wait: see role3_cov)
   }
   __syncthreads();
   store_tiles3<F, NTHR>(a, c, threadIdx.x);
@@ -800,11 +800,11 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
     // the update barrier on, and the LSU and the FP64 pipe take turns idling.
     if (n > 1) __nanosleep((unsigned)(ESKF3_STAGGER_NS * (ct >> 5)));
 #endif
+#ifndef ESKF_EXP_NO_PIPE
+    if (n > 0) fx_slot_wait(c.mbar, k);  // the Jacobian record of the first step of the epoch is complete
+#endif
     for (int it = 0; it < n; ++it) {
       const int64_t kk = k + it;
-#ifndef ESKF_EXP_NO_PIPE
-      fx_slot_wait(c.mbar, kk);  // the Jacobian record of step kk is complete
-#endif
       if (ESKF3_COV_ON) {
         const d2* f2 = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
         // pass 1: T(:, 3g..3g+2) = Fx P(:, 3g..3g+2), rows stored as they are finished
@@ -812,6 +812,11 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
         fx3_apply_store<F, RS3>(X, f2, Tb + 3 * cg);
         __syncwarp(gmask);
         load_rows();  // X[k][v] = T(3g+v, k)
+#ifndef ESKF_EXP_NO_PIPE
+        // the record of the NEXT step is waited for here, behind the latency of the transposed reload, so that
+        // nothing stands between the end of this step and the first coefficient fetch of the next one
+        if (it + 1 < n) fx_slot_wait(c.mbar, kk + 1);
+#endif
         __syncwarp(gmask);
 #else  // (profiling experiment: the arithmetic of pass 1 without the shared-memory transposition; wrong results)
         fx3_apply_inplace<F>(X, f2);
@@ -836,7 +841,6 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
 #ifdef ESKF_EXP_NO_UPDATE  // (profiling experiment: propagation only)
     __syncthreads();
     if (cg == 0) sxw[SX3_OK2 * F] = 0.0;
-    __syncthreads();
     __syncthreads();
     continue;
 #endif
@@ -869,9 +873,10 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
       __syncwarp(gmask);
       const double dth[3] = {sxc[(SX3_DELTA + 6) * F], sxc[(SX3_DELTA + 7) * F], sxc[(SX3_DELTA + 8) * F]};
       const double dthc[3] = {sxc[(SX3_DELTA + 21) * F], sxc[(SX3_DELTA + 22) * F], sxc[(SX3_DELTA + 23) * F]};
-      upd3_finish<4>(X, cg, rec, rd, dth, dthc);
+      upd3_finish<4, F>(X, cg, rec, sxc + SX3_RD * F, dth, dthc);
     }
-    __syncthreads();  // U2 done
+    // no CTA barrier here: the scalar roles go on to the first steps of the next epoch while the covariance warps
+    // finish the Joseph form (what they exchange next is ordered by the record pipeline and by the next U0 | U1)
   }
   dump_rows();
   __syncthreads();

@@ -147,7 +147,7 @@ int hc_update3(const double* model, double* x, double* P, const double* u, const
   }
   inject_error(m, s, delta);
   for (int g = 0; g < 8; ++g) upd3_w_pass<1>(X[g], g, rec);
-  for (int g = 0; g < 8; ++g) upd3_finish<1>(X[g], g, rec, rd, delta + 6, delta + 21);
+  for (int g = 0; g < 8; ++g) upd3_finish<1, 1>(X[g], g, rec, rd, delta + 6, delta + 21);
   for (int g = 0; g < 8; ++g)
     for (int i = 0; i < 24; ++i) for (int v = 0; v < 3; ++v) P[(3 * g + v) * 24 + i] = X[g][i][v];
   store_nominal(s, x, uu, RR);
