@@ -4,8 +4,9 @@
 // One CTA owns F filters for a whole launch (a whole trajectory in eskf_run).  Warps are roles:
 //   warp 0  IMU     lane = filter: p, v, q of the nominal state (Filter._predict_nominal, Filter.py:232-247,
 //                   equations.py:72-86) and R_WB_old (Filter.py:227)
-//   warp 1  CAMERA  lane = filter: p_cam, q_cam (equations.py:88-98), the measurement residual
-//                   (Filter.py:363-375), status word
+//   warp 1  CAMERA  lane = filter: p_cam, q_cam (equations.py:88-98), rows 18:21 of Fx (Filter.py:283-321, second half of
+//                   the Jacobian work: it waits for JACOB's probe kinematics of the step at a two-warp barrier),
+//                   the measurement residual (Filter.py:363-375), status word
 //   warp 3  JACOB   lane = filter: dofs, notch chain, probe forward kinematics (Probe.py:470-480) and the
 //                   Jacobian blocks of Fx / Fi (Filter._predict_error, Filter.py:249-342)
 //   warp 2  STAGER  lane = filter: stages the IMU sample stream (dt, om, acc) into a 4-slot shared-memory
@@ -58,17 +59,18 @@ constexpr int SX3_RING = 0;     // 4 x 8: om(3) acc(3) dt pad
 constexpr int SX3_RO = 32;      // 2 x 9
 constexpr int SX3_RW = 50;      // 2 x 9
 constexpr int SX3_V = 68;       // 2 x 3
-constexpr int SX3_PK = 74;      // 2 x 17: p(3) R(9) z6(3) notch notch'
-constexpr int SX3_MEAS = 108;   // 8: cam pos(3) quat(4) notch
-constexpr int SX3_RES = 116;    // 7: measurement residual            CAMERA -> COVARIANCE
-constexpr int SX3_OK = 123;     // residual valid
-constexpr int SX3_DELTA = 124;  // 24: error state K res              COVARIANCE -> scalar roles
-constexpr int SX3_OK2 = 148;    // update applied
-constexpr int SX3_QD = 149;     // 13: diag(Q)
-constexpr int SX3_RD = 162;     // 7: diag(R)
-constexpr int SX3_ST = 169;     // 12: statistics partials (epilogue)
-constexpr int SX3_TR = 182;     // 24: trigonometry cache of the probe kinematics (private to JACOB)
-constexpr int SX3_SIZE = 206;
+constexpr int PK3 = 20;         // PK slot: p(3) R(9) z6(3) notch notch' dofs[3..5]
+constexpr int SX3_PK = 74;      // 2 x PK3
+constexpr int SX3_MEAS = 114;   // 8: cam pos(3) quat(4) notch
+constexpr int SX3_RES = 122;    // 7: measurement residual            CAMERA -> COVARIANCE
+constexpr int SX3_OK = 129;     // residual valid
+constexpr int SX3_DELTA = 130;  // 24: error state K res              COVARIANCE -> scalar roles
+constexpr int SX3_OK2 = 154;    // update applied
+constexpr int SX3_QD = 155;     // 13: diag(Q)
+constexpr int SX3_RD = 168;     // 7: diag(R)
+constexpr int SX3_ST = 175;     // 12: statistics partials (epilogue)
+constexpr int SX3_TR = 187;     // 24: trigonometry cache of the probe kinematics (JACOB writes, CAMERA reads)
+constexpr int SX3_SIZE = 212;
 
 template <int F>
 struct Lay3 {
@@ -146,6 +148,9 @@ __device__ __forceinline__ void fx_slot_wait(uint64_t* mbar, int64_t kk) {  // c
 __device__ __forceinline__ void fx_slot_release(uint64_t* mbar, int64_t kk) { mbar_arrive_warp(mbar + 2 + (kk & 1)); }
 // barrier of the four scalar-role warps
 __device__ __forceinline__ void scalar_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// JACOB -> CAMERA inside a step: the probe kinematics of the step are published (JACOB does not wait)
+__device__ __forceinline__ void pk_ready_arrive() { asm volatile("bar.arrive 2, 64;" ::: "memory"); }
+__device__ __forceinline__ void pk_ready_wait() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
 
 struct Ctx3 {
   double* smem;
@@ -350,11 +355,16 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
   using L = Lay3<F>;
   const bool act = lane < c.nf;
   double* sx = c.smem + L::SX + lane;
-  double pc[3], qc[4];
+  d2* fxb = reinterpret_cast<d2*>(c.smem + L::FXB) + lane;  // pair j2 of slot s at fxb[(s * FX3_NPAIR + j2) * F]
+  const TRView<F> trv{sx + SX3_TR * F};
+  double pc[3], qc[4], sig_om[3] = {0, 0, 0};
   double mse_last = 0.0, mse_sum = 0.0, n_upd = 0.0;
   int32_t st = 0;
   if (act) {
     const double* xg = a.x + (c.f0 + lane) * NX;
+    const double* pg = a.par + (c.f0 + lane) * PAR_STRIDE;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) sig_om[i] = pg[PAR_SIGOM + i];
 #pragma unroll
     for (int i = 0; i < 3; ++i) pc[i] = xg[19 + i];
 #pragma unroll
@@ -366,8 +376,9 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
     for (int it = 0; it < n; ++it) {
+      const int64_t kk = k + it;
+      fx_slot_acquire(c.mbar, kk);  // the covariance warps are done with the record of step kk - 2
       if (act && ESKF3_SCALAR_ON(it)) {
-        const int64_t kk = k + it;
         const double* uo = sx + (SX3_RING + 8 * (int)(kk & 3)) * F;
         const double* un = sx + (SX3_RING + 8 * (int)((kk + 1) & 3)) * F;
         const int s = (int)(kk & 1);
@@ -377,18 +388,41 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
           om_old[i] = uo[i * F];
           om[i] = un[i * F];
           vpre[i] = sx[(SX3_V + 3 * s + i) * F];
-          pkp[i] = sx[(SX3_PK + 17 * s + i) * F];
-          pkz[i] = sx[(SX3_PK + 17 * s + 12 + i) * F];
+          pkp[i] = sx[(SX3_PK + PK3 * s + i) * F];
+          pkz[i] = sx[(SX3_PK + PK3 * s + 12 + i) * F];
         }
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
           Rwb[i] = sx[(SX3_RW + 9 * s + i) * F];
-          pkR[i] = sx[(SX3_PK + 17 * s + 3 + i) * F];
+          pkR[i] = sx[(SX3_PK + PK3 * s + 3 + i) * F];
         }
         const double dt = un[6 * F];
-        const double notch_d = sx[(SX3_PK + 17 * s + 16) * F];
+        const double notch_d = sx[(SX3_PK + PK3 * s + 16) * F];
         cam_nominal_step(pc, qc, vpre, Rwb, dt, om_old, om, pkp, pkR, pkz, notch_d);
       }
+      pk_ready_wait();  // JACOB has published the probe kinematics of the post-predict (dofs, notch): PK slot sn, TR
+      if (act && ESKF3_SCALAR_ON(it)) {
+        // rows 18:21 of Fx (Filter._cam_error_jacobian, Filter.py:270-342): the half of the Jacobian work that
+        // only needs the probe kinematics, R_WB_old and om_old -- taken off JACOB, the longest scalar role
+        const double* uo = sx + (SX3_RING + 8 * (int)(kk & 3)) * F;
+        const double dt = sx[(SX3_RING + 8 * (int)((kk + 1) & 3) + 6) * F];
+        const int s = (int)(kk & 1), sn = s ^ 1;
+        const PKView<F> pk{sx + (SX3_PK + PK3 * sn) * F};
+        double om_old[3], Ro[9], dofs[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          om_old[i] = uo[i * F];
+          dofs[3 + i] = sx[(SX3_PK + PK3 * sn + 17 + i) * F];
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Ro[i] = sx[(SX3_RO + 9 * s + i) * F];
+        double fx[FX3_SIZE];
+        jac_rows_h1(a.model, dofs, pk, trv, Ro, dt, om_old, sig_om, fx);
+        d2* dst = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
+#pragma unroll
+        for (int j = FX3_H1 / 2; j < FX3_AB / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
+      }
+      fx_slot_publish(c.mbar, kk);  // rows 18:21 of the record of step kk are in place
       scalar_barrier();
     }
     k += n;
@@ -402,7 +436,7 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
 #pragma unroll
         for (int i = 0; i < 7; ++i) cam[i] = sx[(SX3_MEAS + i) * F];
         const double notch_meas = sx[(SX3_MEAS + 7) * F];
-        const double notch0 = sx[(SX3_PK + 17 * (int)(k & 1) + 15) * F];
+        const double notch0 = sx[(SX3_PK + PK3 * (int)(k & 1) + 15) * F];
         Nominal s;  // only pc, qc, notch[0] are read by update_residual
 #pragma unroll
         for (int i = 0; i < 3; ++i) s.pc[i] = pc[i];
@@ -465,7 +499,8 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
 }
 
 // ---------------------------------------------------------------------------------------------
-// role 2: dofs / notch, probe kinematics, Jacobian blocks (rows 18:24; rows 3:9 come from the IMU role).
+// role 2: dofs / notch, probe kinematics, Jacobian blocks (rows 21:24 and the noise rows; rows 3:9 come from the IMU
+// role, rows 18:21 from the CAMERA role).
 // The probe kinematics and their trigonometry cache live in shared memory (PK slots, TR), not in registers.
 template <int F, int NTHR>
 __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lane) {
@@ -474,10 +509,12 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
   double* sx = c.smem + L::SX + lane;
   d2* fxb = reinterpret_cast<d2*>(c.smem + L::FXB) + lane;  // pair j2 of slot s at fxb[(s * FX3_NPAIR + j2) * F]
   const TRView<F> trv{sx + SX3_TR * F};
-  auto pkv = [&](int s) { return PKView<F>{sx + (SX3_PK + 17 * s) * F}; };
-  auto put_notch = [&](int s, const double* notch) {
-    sx[(SX3_PK + 17 * s + 15) * F] = notch[0];
-    sx[(SX3_PK + 17 * s + 16) * F] = notch[1];
+  auto pkv = [&](int s) { return PKView<F>{sx + (SX3_PK + PK3 * s) * F}; };
+  auto put_notch = [&](int s, const double* notch, const double* dofs) {  // the scalars that go with a PK slot
+    sx[(SX3_PK + PK3 * s + 15) * F] = notch[0];
+    sx[(SX3_PK + PK3 * s + 16) * F] = notch[1];
+#pragma unroll
+    for (int i = 3; i < 6; ++i) sx[(SX3_PK + PK3 * s + 14 + i) * F] = dofs[i];
   };
   double dofs[6], notch[3], sig_om[3] = {0, 0, 0};
   bool imu_q = false;
@@ -495,7 +532,7 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
 #pragma unroll
     for (int j = 0; j < 4; ++j) trv.ang(j) = __longlong_as_double(0x7ff8000000000000LL);  // nothing cached yet
     probe_update_v(a.model, dofs, notch, pkv(0), trv);
-    put_notch(0, notch);
+    put_notch(0, notch, dofs);
   }
   __syncthreads();  // prologue
   int64_t k = 0;
@@ -517,28 +554,32 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
 #pragma unroll
           for (int i = 0; i < PK_SIZE; ++i) pk.b[i * F] = po.b[i * F];
         }
-        put_notch(sn, notch);
-        double om_old[3], Ro[9];
+        put_notch(sn, notch, dofs);
+      }
+      pk_ready_arrive();  // the CAMERA warp takes rows 18:21 from here
+      if (act && ESKF3_SCALAR_ON(it)) {
+        const double* uo = sx + (SX3_RING + 8 * (int)(kk & 3)) * F;
+        const double dt = sx[(SX3_RING + 8 * (int)((kk + 1) & 3) + 6) * F];
+        const int s = (int)(kk & 1), sn = s ^ 1;
+        const PKView<F> pk = pkv(sn);
+        double om_old[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) om_old[i] = uo[i * F];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Ro[i] = sx[(SX3_RO + 9 * s + i) * F];
         d2* dst = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
         double fx[FX3_SIZE];
-        // every row group is shipped as soon as it is final (short register live ranges)
         jac_rows_h2(a.model, notch[1], pk, trv, dt, om_old, sig_om, fx);
 #pragma unroll
         for (int j = 0; j < FX3_H1 / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
-        jac_rows_h1(a.model, dofs, pk, trv, Ro, dt, om_old, sig_om, fx);
-#pragma unroll
-        for (int j = FX3_H1 / 2; j < FX3_AB / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
         if (imu_q) {
+          double Ro[9];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) Ro[i] = sx[(SX3_RO + 9 * s + i) * F];
           jac_rows_noise(pk, Ro, dt, fx);
 #pragma unroll
           for (int j = FX3_NPAIR_MAIN; j < FX3_NPAIR; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
         }
       }
-      fx_slot_publish(c.mbar, kk);  // dt, rows 18:24 (and the noise rows) of the record of step kk are in place
+      fx_slot_publish(c.mbar, kk);  // dt, rows 21:24 (and the noise rows) of the record of step kk are in place
       scalar_barrier();
     }
     k += n;
@@ -554,7 +595,7 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
 #pragma unroll
         for (int i = 0; i < 3; ++i) notch[i] += sx[(SX3_DELTA + 15 + i) * F];
         probe_update_v(a.model, dofs, notch, pkv((int)(k & 1)), trv);
-        put_notch((int)(k & 1), notch);
+        put_notch((int)(k & 1), notch, dofs);
       }
     }
     scalar_barrier();  // U2 of the scalar roles done (the covariance warps do not wait: see role3_cov)
@@ -900,8 +941,8 @@ __global__ void __launch_bounds__(128 + 8 * F, 1) eskf_kernel3(const __grid_cons
   c.dtp = a.dt ? a.dt + c.traj * a.T : nullptr;
   c.mbar = reinterpret_cast<uint64_t*>(smem + L::MBAR);
   if (tid == 0) {
-    mbar_init(c.mbar + 0, 2);      // full[s]:  the IMU and the JACOB warp
-    mbar_init(c.mbar + 1, 2);
+    mbar_init(c.mbar + 0, 3);      // full[s]:  the IMU, the CAMERA and the JACOB warp (rows 3:9, 18:21, 21:24)
+    mbar_init(c.mbar + 1, 3);
     mbar_init(c.mbar + 2, F / 4);  // empty[s]: the covariance warps
     mbar_init(c.mbar + 3, F / 4);
   }
