@@ -850,9 +850,9 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
         const d2* f2 = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
         // pass 1: T(:, 3g..3g+2) = Fx P(:, 3g..3g+2), rows stored as they are finished
 #ifndef ESKF_EXP_NO_TRANSPOSE
-        fx3_apply_store<F, RS3>(X, f2, Tb + 3 * cg);
+        fx3_apply_store<F, RS3, false>(X, f2, Tb + 3 * cg);
         __syncwarp(gmask);
-        load_rows();  // X[k][v] = T(3g+v, k)
+        if (!fx3_reload_skips_lane(cg)) load_rows();  // X[k][v] = T(3g+v, k); lanes 3, 4: their own tile is that already
 #ifndef ESKF_EXP_NO_PIPE
         // the record of the NEXT step is waited for here, behind the latency of the transposed reload, so that
         // nothing stands between the end of this step and the first coefficient fetch of the next one

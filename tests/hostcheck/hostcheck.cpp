@@ -105,11 +105,12 @@ void hc_propagate3(const double* model, double* x, double* P, double* u, double*
   double T[24][24];
   for (int g = 0; g < 8; ++g) {
     for (int i = 0; i < 24; ++i) for (int v = 0; v < 3; ++v) X[g][i][v] = P[i * 24 + 3 * g + v];
-    fx3_apply_store<1, 24>(X[g], f2, &T[0][0] + 3 * g);
+    fx3_apply_store<1, 24, false>(X[g], f2, &T[0][0] + 3 * g);  // the identity rows 9:15 are not exchanged ...
   }
   auto qdf = [&](int j) { return qd[j]; };
   for (int g = 0; g < 8; ++g) {
-    for (int k = 0; k < 24; ++k) for (int v = 0; v < 3; ++v) X[g][k][v] = T[3 * g + v][k];
+    if (!fx3_reload_skips_lane(g))  // ... lanes 3 and 4 keep their own tile instead (symmetry of P)
+      for (int k = 0; k < 24; ++k) for (int v = 0; v < 3; ++v) X[g][k][v] = T[3 * g + v][k];
     fx3_apply_inplace<1>(X[g], f2);
     double qdv[3];
     fx3_noise_diag(g, qdf, qdv);
