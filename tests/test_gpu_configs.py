@@ -1,0 +1,85 @@
+"""BASELINE.json configurations 3 and 4 as parity cases (they are not bench lines):
+  config 3 -- noise / tuning sweep: every filter has its own Q, R and P0 (per-filter parameter rows);
+  config 4 -- all data/trajs trajectories stacked in one launch, 33 IMU samples per camera frame (1 kHz / 30 Hz),
+              several filters per trajectory, each CTA following its own trajectory's epoch structure."""
+import numpy as np
+import pytest
+
+from tests.helpers import Scenario, cov_err, mandala_scenario, model_kwargs, state_err
+from oracle.eskf_oracle import OracleConfig
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_oracle(sc, x0=None, P0=None, Qd=None, Rd=None):
+    kf = sc.new_oracle(x0, P0)
+    if Qd is not None:
+        kf.Q = np.diag(Qd)
+    if Rd is not None:
+        kf.R = np.diag(Rd)
+    k = 0
+    for e in range(len(sc.n_prop)):
+        for _ in range(sc.n_prop[e]):
+            kf.propagate(sc.dt[k], sc.om_acc[k, :3], sc.om_acc[k, 3:])
+            k += 1
+        kf.update(sc.cam_meas[e, :3], sc.cam_meas[e, 3:], sc.notch_meas[e])
+    return kf
+
+
+@pytest.mark.parametrize("variant", [3, 1])
+def test_config3_tuning_sweep_per_filter_q_r_p0(golden, variant):
+    from dvi_ekf_b200 import BatchFilter
+
+    sc = mandala_scenario(golden, n_frames=8, ifv=10)
+    n = 36  # 3 x 3 x 4 grid: random-walk scale, measurement-noise scale, P0 scale (+ ragged CTA)
+    qs = np.logspace(-2, 2, 3)
+    rs = np.logspace(-3, 3, 3)
+    ps = np.logspace(-1, 1, 4)
+    grid = [(a, b, c) for a in qs for b in rs for c in ps]
+    Qd = np.array([sc.Qd * np.hstack((np.ones(6), np.full(7, a))) for a, b, c in grid])
+    Rd = np.array([sc.Rd * b for a, b, c in grid])
+    P0 = np.array([sc.P0 * c for a, b, c in grid])
+    with BatchFilter(n, variant=variant, **model_kwargs(sc.cfg)) as bf:
+        bf.set_noise(Qd, Rd, sc.sig_om[None])
+        bf.set_state(sc.x0[None], P0, sc.u0[None], None)
+        st, sm = bf.run(sc.dt, sc.om_acc, sc.n_prop, sc.cam_meas, sc.notch_meas)
+        xg, Pg, ug, Rg, status = bf.get_state()
+    assert np.all(status == 0) and sm[11] == n
+    worst_s = worst_P = 0.0
+    for i in (0, 5, 13, 22, 35):
+        kf = _run_oracle(sc, P0=P0[i], Qd=Qd[i], Rd=Rd[i])
+        xr, Pr, _, _ = kf.get_vectors()
+        worst_s = max(worst_s, state_err(xg[i], xr))
+        worst_P = max(worst_P, cov_err(Pg[i], Pr, Rd[i]))
+    assert worst_s < 1e-8 and worst_P < 1e-8, (worst_s, worst_P)  # free-running, 70 steps
+    assert np.abs(xg[0] - xg[35]).max() > 1e-9  # the tuning really changes the estimate
+
+
+@pytest.mark.parametrize("variant,fpt", [(3, 8), (3, 28), (1, 12)])
+def test_config4_stacked_trajectories_33_samples_per_frame(golden, variant, fpt):
+    from dvi_ekf_b200 import BatchFilter
+
+    names = ["traj_trans_x", "traj_rot_z", "traj_from_prop", "traj_mandala0_gt"]
+    frames, ifv = 7, 33
+    scs = [Scenario(golden[nm][:frames], OracleConfig(max_vals=frames, interframe_vals=ifv)) for nm in names]
+    T, E = len(scs[0].dt), len(scs[0].n_prop)
+    assert all(len(s.dt) == T and len(s.n_prop) == E for s in scs)
+    cat = lambda f: np.concatenate([f(s) for s in scs])
+    n = fpt * len(scs)
+    x0 = np.concatenate([np.repeat(s.x0[None], fpt, 0) for s in scs])
+    u0 = np.concatenate([np.repeat(s.u0[None], fpt, 0) for s in scs])
+    sc0 = scs[0]
+    with BatchFilter(n, variant=variant, **model_kwargs(sc0.cfg)) as bf:
+        bf.set_noise(sc0.Qd[None], sc0.Rd[None], sc0.sig_om[None])
+        bf.set_state(x0, sc0.P0[None], u0, None)
+        st, sm = bf.run(cat(lambda s: s.dt), cat(lambda s: s.om_acc), cat(lambda s: s.n_prop), cat(lambda s: s.cam_meas),
+                        cat(lambda s: s.notch_meas), n_traj=len(scs), filters_per_traj=fpt)
+        xg, Pg, ug, Rg, status = bf.get_state()
+    assert np.all(status == 0) and sm[11] == n and np.allclose(st[:, 9], E)
+    for j, s in enumerate(scs):
+        kf = _run_oracle(s)
+        xr, Pr, ur, Rr = kf.get_vectors()
+        for i in (j * fpt, (j + 1) * fpt - 1):
+            assert state_err(xg[i], xr) < 1e-8, (names[j], state_err(xg[i], xr))  # free-running, 198 steps
+            assert cov_err(Pg[i], Pr, s.Rd) < 1e-8, (names[j], cov_err(Pg[i], Pr, s.Rd))
+            assert np.abs(ug[i] - ur).max() < 1e-12
