@@ -83,7 +83,7 @@ thread_local std::string g_err;
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-constexpr int N_STAGE = 8;
+constexpr int N_STAGE = 9;
 struct eskf_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -92,8 +92,8 @@ struct eskf_handle {
   double *x = nullptr, *P = nullptr, *u = nullptr, *Ro = nullptr, *par = nullptr;
   int32_t* status = nullptr;
   // grow-only device staging for host-side arguments / results
-  void* stage[N_STAGE] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t stage_sz[N_STAGE] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void* stage[N_STAGE] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t stage_sz[N_STAGE] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   double* stats_sum_dev = nullptr;
   int64_t launches = 0;
   int fpc = 0;  // filters per CTA (0 = automatic)
@@ -430,6 +430,16 @@ int eskf_run(eskf_t* h, const eskf_streams_t* sp, double* stats_out, double* sta
       dstats = (double*)h->stage[7];
     }
   }
+  double* dtrace = nullptr;
+  const size_t tb = (size_t)h->N * (size_t)T * NX * sizeof(double);
+  if (sp->trace_x) {
+    if (smem_kind == ESKF_MEM_DEVICE) {
+      dtrace = sp->trace_x;
+    } else {
+      if ((rc = stage_reserve(h, 8, tb))) return rc;
+      dtrace = (double*)h->stage[8];
+    }
+  }
   double* dsum = nullptr;
   if (stats_sum) {
     dsum = (mem == ESKF_MEM_DEVICE) ? stats_sum : h->stats_sum_dev;
@@ -453,6 +463,7 @@ int eskf_run(eskf_t* h, const eskf_streams_t* sp, double* stats_out, double* sta
   a.do_update = 1;
   a.stats_out = dstats;
   a.stats_sum = dsum;
+  a.trace = dtrace;
   a.seed = sp->seed;
   a.noise_free0 = sp->noise_free_filter0;
   for (int i = 0; i < 6; ++i) {
@@ -464,6 +475,10 @@ int eskf_run(eskf_t* h, const eskf_streams_t* sp, double* stats_out, double* sta
     if (a.cam_noise[i] != 0.0) a.noise_on = 1;
   }
   if ((rc = launch(h, a, fpt, nt > 1))) return rc;
+  if (dtrace && smem_kind == ESKF_MEM_HOST) {
+    CK(cudaMemcpyAsync(sp->trace_x, dtrace, tb, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
   if (mem == ESKF_MEM_HOST && (stats_out || stats_sum)) {
     if (stats_out) CK(cudaMemcpyAsync(stats_out, dstats, sb, cudaMemcpyDeviceToHost, h->stream));
     if (stats_sum) CK(cudaMemcpyAsync(stats_sum, dsum, ESKF_NSTAT * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

@@ -56,12 +56,31 @@ struct KArgs {
   double* K_out;
   double* stats_out;
   double* stats_sum;
+  double* trace;  // [N,T,26] or nullptr
   uint64_t seed;
   double imu_noise[6];
   double cam_noise[7];
   int noise_on;
   int noise_free0;
 };
+
+// one FilterTraj row's worth of nominal state in the layout of x (include/eskf.h)
+__device__ __forceinline__ void trace_row(double* r, const Nominal& s) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    r[i] = s.p[i];
+    r[3 + i] = s.v[i];
+    r[16 + i] = s.notch[i];
+    r[19 + i] = s.pc[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r[6 + i] = s.q[i];
+    r[22 + i] = s.qc[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) r[10 + i] = s.dofs[i];
+}
 
 __device__ __forceinline__ void euler_xyz_deg(const double* q, double* e) {
   // Rotation.as_euler("xyz", degrees=True) away from gimbal lock (Quaternion.py:121-123)
@@ -274,6 +293,7 @@ __global__ void __launch_bounds__(32 + 8 * F, 1) eskf_kernel(const __grid_consta
           propagate_scalar(a.model, s, pk, ptr, Rq, dt, om, acc, sig_om, imu_q,
                            sScr + tid * SCR_STRIDE + (it & 1) * FX_STRIDE);
 #endif
+          if (a.trace) trace_row(a.trace + ((f0 + tid) * a.T + kk) * NX, s);
         }
       } else if (it >= 1) {
 #ifndef ESKF_EXP_NO_COV  // (profiling experiment switch: time the scalar role alone)
@@ -350,6 +370,7 @@ __global__ void __launch_bounds__(32 + 8 * F, 1) eskf_kernel(const __grid_consta
           probe_update(a.model, s.dofs, s.notch, pk, ptr);
           after_update = true;
           n_upd += 1.0;
+          if (a.trace && k > 0) trace_row(a.trace + ((f0 + tid) * a.T + k - 1) * NX, s);  // FilterTraj.append_updated_states
         } else {
           st |= ESKF_STATUS_UPDATE_SKIPPED;
         }

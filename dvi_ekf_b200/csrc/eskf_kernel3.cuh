@@ -214,6 +214,29 @@ __device__ __forceinline__ void write_stats3(const KArgs& a, const Ctx3& c, int 
   }
 }
 
+// trace mode (eskf_streams_t.trace_x): every role files its part of the FilterTraj row
+__device__ __forceinline__ void trace_pvq(double* r, const double* p, const double* v, const double* q) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    r[i] = p[i];
+    r[3 + i] = v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[6 + i] = q[i];
+}
+__device__ __forceinline__ void trace_cam(double* r, const double* pc, const double* qc) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) r[19 + i] = pc[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r[22 + i] = qc[i];
+}
+__device__ __forceinline__ void trace_dofs(double* r, const double* dofs, const double* notch) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) r[10 + i] = dofs[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) r[16 + i] = notch[i];
+}
+
 // ---------------------------------------------------------------------------------------------
 // role 0: IMU nominal state
 template <int F, int NTHR>
@@ -270,6 +293,7 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
           for (int j = FX3_AB / 2; j < FX3_MAIN / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
         }
         imu_nominal_step(p, v, q, Rwb, dt, om_old, acc_old, om, acc, Rold);
+        if (a.trace) trace_pvq(a.trace + ((c.f0 + lane) * a.T + kk) * NX, p, v, q);
         const int s = (int)((kk + 1) & 1);
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
@@ -302,6 +326,7 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
 #pragma unroll
         for (int i = 0; i < 4; ++i) q[i] = qn[i];
         quat_to_rot(q, Rwb);  // R_WB of the next step; R_WB_old keeps the pre-update value (quirk Q8)
+        if (a.trace && k > 0) trace_pvq(a.trace + ((c.f0 + lane) * a.T + k - 1) * NX, p, v, q);  // FilterTraj.append_updated_states
         const int s = (int)(k & 1);
 #pragma unroll
         for (int i = 0; i < 9; ++i) sx[(SX3_RW + 9 * s + i) * F] = Rwb[i];
@@ -399,6 +424,7 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
         const double dt = un[6 * F];
         const double notch_d = sx[(SX3_PK + PK3 * s + 16) * F];
         cam_nominal_step(pc, qc, vpre, Rwb, dt, om_old, om, pkp, pkR, pkz, notch_d);
+        if (a.trace) trace_cam(a.trace + ((c.f0 + lane) * a.T + kk) * NX, pc, qc);
       }
       pk_ready_wait();  // JACOB has published the probe kinematics of the post-predict (dofs, notch): PK slot sn, TR
       if (act && ESKF3_SCALAR_ON(it)) {
@@ -464,6 +490,7 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
 #pragma unroll
         for (int i = 0; i < 4; ++i) qc[i] = qn[i];
         n_upd += 1.0;
+        if (a.trace && k > 0) trace_cam(a.trace + ((c.f0 + lane) * a.T + k - 1) * NX, pc, qc);
       } else {
         st |= ESKF_STATUS_UPDATE_SKIPPED;
       }
@@ -555,6 +582,7 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
           for (int i = 0; i < PK_SIZE; ++i) pk.b[i * F] = po.b[i * F];
         }
         put_notch(sn, notch, dofs);
+        if (a.trace) trace_dofs(a.trace + ((c.f0 + lane) * a.T + kk) * NX, dofs, notch);
       }
       pk_ready_arrive();  // the CAMERA warp takes rows 18:21 from here
       if (act && ESKF3_SCALAR_ON(it)) {
@@ -596,6 +624,7 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
         for (int i = 0; i < 3; ++i) notch[i] += sx[(SX3_DELTA + 15 + i) * F];
         probe_update_v(a.model, dofs, notch, pkv((int)(k & 1)), trv);
         put_notch((int)(k & 1), notch, dofs);
+        if (a.trace && k > 0) trace_dofs(a.trace + ((c.f0 + lane) * a.T + k - 1) * NX, dofs, notch);
       }
     }
     scalar_barrier();  // U2 of the scalar roles done (the covariance warps do not wait: see role3_cov)

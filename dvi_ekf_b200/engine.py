@@ -188,9 +188,11 @@ class BatchFilter:
     def run(self, dt, om_acc, n_prop, cam, notch, cam_ref=None, imu_ref=None, gt_dofs=(0, 0, 0, 0, 0, 20.0),
             n_traj: int = 1, filters_per_traj: Optional[int] = None, seed: int = 0, filter_id0: int = 0,
             imu_noise_std=None, cam_noise_std=None, noise_free_filter0: bool = True, want_stats: bool = True,
-            stats_on_device: bool = False):
+            stats_on_device: bool = False, trace=None):
         """``Filter.run`` (Filter.py:144-185) for every filter, in one persistent kernel.
-        Returns (stats [N,16], stats_sum [16]) (see include/eskf.h) or None."""
+        Returns (stats [N,16], stats_sum [16]) (see include/eskf.h) or None.
+        ``trace``: optional [N,T,26] float64 array (numpy for host streams, CUDA tensor for device streams) that
+        receives the nominal state after every IMU step, updated state at the update instants (FilterTraj rows)."""
         adt = _Arg(dt, None, name="dt")
         anp = _Arg(n_prop, None, dtype=np.int32, name="n_prop")
         T = adt.rows // n_traj
@@ -210,6 +212,15 @@ class BatchFilter:
         s.imu_noise_std = (C.c_double * 6)(*([0.0] * 6 if imu_noise_std is None else [float(v) for v in imu_noise_std]))
         s.cam_noise_std = (C.c_double * 7)(*([0.0] * 7 if cam_noise_std is None else [float(v) for v in cam_noise_std]))
         s.noise_free_filter0 = 1 if noise_free_filter0 else 0
+        if trace is not None:
+            if tuple(trace.shape) != (self.n, T, 26):
+                raise ValueError(f"trace must have shape {(self.n, T, 26)}")
+            if isinstance(trace, np.ndarray) and not (trace.flags.c_contiguous and trace.dtype == np.float64):
+                raise TypeError("trace must be a C-contiguous float64 array (it is written in place)")
+            atr = _Arg(trace.reshape(self.n * T, 26), 26, name="trace")
+            if atr.mem != mem:
+                raise ValueError("trace must live where the streams live (host numpy / CUDA tensor)")
+            s.trace_x = atr.ptr
         if not want_stats:
             check(self._lib.eskf_run(self._h, C.byref(s), None, None, MEM_HOST), "eskf_run")
             return None

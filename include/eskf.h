@@ -81,6 +81,10 @@ typedef struct {
   double cam_noise_std[7];  /* added to camera position(3), as small rotation(3), notch(1) */
   int32_t noise_free_filter0; /* global filter 0 stays noise free (= the oracle run) */
   int32_t reserved;
+  /* trace mode (nullable, in `mem` space): [N,T,26] nominal state after every IMU step, the row of the last step
+   * of an epoch holding the UPDATED state -- the rows FilterTraj keeps (FilterTraj.py:34-69, Filter.py:229,382).
+   * 208 B per filter-step: a diagnostic / export mode, HBM bound, not the production path. */
+  double* trace_x;
 } eskf_streams_t;
 
 #define ESKF_NSTAT 16

@@ -83,3 +83,53 @@ def test_config4_stacked_trajectories_33_samples_per_frame(golden, variant, fpt)
             assert state_err(xg[i], xr) < 1e-8, (names[j], state_err(xg[i], xr))  # free-running, 198 steps
             assert cov_err(Pg[i], Pr, s.Rd) < 1e-8, (names[j], cov_err(Pg[i], Pr, s.Rd))
             assert np.abs(ug[i] - ur).max() < 1e-12
+
+
+@pytest.mark.parametrize("variant", [3, 1])
+def test_trace_mode_reproduces_the_reference_golden_file_through_eskf_run(golden, variant, tmp_path):
+    """one persistent launch with trace_x, the FilterTraj rows written with the reference's text format
+    (files.py:68-82) and read back: every number of kf_best_mandala0_mono.txt to its 9 printed decimals."""
+    from dvi_ekf_b200 import BatchFilter
+    from dvi_ekf_b200.trace import save_filter_traj
+
+    sc = mandala_scenario(golden, n_frames=10, ifv=1, zero_frozen_dofs=False, euler_mode="zyx_legacy")
+    n, T = 5, len(sc.dt)
+    trace = np.full((n, T, 26), np.nan)
+    with BatchFilter(n, variant=variant, **model_kwargs(sc.cfg)) as bf:
+        bf.set_noise(sc.Qd[None], sc.Rd[None], sc.sig_om[None])
+        bf.set_state(sc.x0[None], sc.P0[None], sc.u0[None], None)
+        bf.run(sc.dt, sc.om_acc, sc.n_prop, sc.cam_meas, sc.notch_meas, trace=trace)
+        xg = bf.get_state()[0]
+    assert np.all(np.isfinite(trace)) and np.array_equal(trace[:, -1], xg)  # last row = final state
+    t_imu = sc.cam.t[1:]  # interframe 1: one IMU step per camera frame
+    fn = tmp_path / "kf_best_mandala0_mono.txt"
+    save_filter_traj(str(fn), sc.cam.t[0], sc.x0, t_imu, trace[n - 1])
+    ours = np.loadtxt(fn)
+    ref = golden["kf_best_mandala0_mono"]
+    assert ours.shape == ref.shape == (10, 30)
+    assert np.abs(ours - ref).max() <= 1.0e-9 + 1e-15  # both sides rounded to 9 decimals
+
+
+def test_trace_mode_rows_between_updates(golden):
+    """interframe 10: rows of propagation steps hold the propagated state, the last row of an epoch the updated one"""
+    from dvi_ekf_b200 import BatchFilter
+
+    sc = mandala_scenario(golden, n_frames=5, ifv=10)
+    T = len(sc.dt)
+    trace = np.zeros((2, T, 26))
+    with BatchFilter(2, **model_kwargs(sc.cfg)) as bf:
+        bf.set_noise(sc.Qd[None], sc.Rd[None], sc.sig_om[None])
+        bf.set_state(sc.x0[None], sc.P0[None], sc.u0[None], None)
+        bf.run(sc.dt, sc.om_acc, sc.n_prop, sc.cam_meas, sc.notch_meas, trace=trace)
+    kf = sc.new_oracle()
+    k = 0
+    worst = 0.0
+    for e in range(len(sc.n_prop)):
+        for j in range(sc.n_prop[e]):
+            kf.propagate(sc.dt[k], sc.om_acc[k, :3], sc.om_acc[k, 3:])
+            if j < sc.n_prop[e] - 1:
+                worst = max(worst, state_err(trace[1, k], kf.get_vectors()[0]))
+            k += 1
+        kf.update(sc.cam_meas[e, :3], sc.cam_meas[e, 3:], sc.notch_meas[e])
+        worst = max(worst, state_err(trace[1, k - 1], kf.get_vectors()[0]))
+    assert worst < 1e-9, worst
