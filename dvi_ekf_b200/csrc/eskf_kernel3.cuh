@@ -137,9 +137,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 // step kk uses record slot kk & 1; its full barrier completes phase kk >> 1, and the slot is free for step kk
 // once the consumers of step kk - 2 have arrived on its empty barrier (phase (kk - 2) >> 1)
 __device__ __forceinline__ void fx_slot_acquire(uint64_t* mbar, int64_t kk) {  // producers, before writing
-#ifndef ESKF_EXP_NO_PIPE
   if (kk >= 2) mbar_wait_relaxed(mbar + 2 + (kk & 1), (uint32_t)(((kk - 2) >> 1) & 1));
-#endif
 }
 __device__ __forceinline__ void fx_slot_publish(uint64_t* mbar, int64_t kk) { mbar_arrive_warp(mbar + (kk & 1)); }
 __device__ __forceinline__ void fx_slot_wait(uint64_t* mbar, int64_t kk) {  // consumers, before reading
@@ -864,33 +862,19 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
   int64_t k = 0;
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
-#ifdef ESKF3_STAGGER_NS
-    // Stagger the covariance warps inside the epoch: they all run the same code on the same amount of data, so
-    // without it their shared-memory phases (transposition stores / loads) and FP64 phases stay aligned from
-    // the update barrier on, and the LSU and the FP64 pipe take turns idling.
-    if (n > 1) __nanosleep((unsigned)(ESKF3_STAGGER_NS * (ct >> 5)));
-#endif
-#ifndef ESKF_EXP_NO_PIPE
     if (n > 0) fx_slot_wait(c.mbar, k);  // the Jacobian record of the first step of the epoch is complete
-#endif
     for (int it = 0; it < n; ++it) {
       const int64_t kk = k + it;
       if (ESKF3_COV_ON) {
         const d2* f2 = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
         // pass 1: T(:, 3g..3g+2) = Fx P(:, 3g..3g+2), rows stored as they are finished
-#ifndef ESKF_EXP_NO_TRANSPOSE
         fx3_apply_store<F, RS3, false>(X, f2, Tb + 3 * cg);
         __syncwarp(gmask);
         if (!fx3_reload_skips_lane(cg)) load_rows();  // X[k][v] = T(3g+v, k); lanes 3, 4: their own tile is that already
-#ifndef ESKF_EXP_NO_PIPE
         // the record of the NEXT step is waited for here, behind the latency of the transposed reload, so that
         // nothing stands between the end of this step and the first coefficient fetch of the next one
         if (it + 1 < n) fx_slot_wait(c.mbar, kk + 1);
-#endif
         __syncwarp(gmask);
-#else  // (profiling experiment: the arithmetic of pass 1 without the shared-memory transposition; wrong results)
-        fx3_apply_inplace<F>(X, f2);
-#endif
         // pass 2: P'(3g+v, :) = Fx T(3g+v, :)^T
         fx3_apply_inplace<F>(X, f2);
         // (the lane index is laundered through an empty asm so that the thirteen selected addends of the diagonal
@@ -901,9 +885,7 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
         fx3_process_noise<F>(X, gl, f2, qdv, qd, imu_q);
 #endif
       }
-#ifndef ESKF_EXP_NO_PIPE
       fx_slot_release(c.mbar, kk);  // this warp is done with the record
-#endif
     }
     k += n;
     if (!a.do_update) continue;
