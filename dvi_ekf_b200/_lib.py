@@ -52,7 +52,7 @@ class EskfStreams(C.Structure):
         ("imu_noise_std", C.c_double * 6),
         ("cam_noise_std", C.c_double * 7),
         ("noise_free_filter0", C.c_int32),
-        ("reserved", C.c_int32),
+        ("noise_id_modulus", C.c_int32),
         ("trace_x", C.c_void_p),
     ]
 

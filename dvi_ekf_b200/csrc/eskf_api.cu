@@ -466,6 +466,7 @@ int eskf_run(eskf_t* h, const eskf_streams_t* sp, double* stats_out, double* sta
   a.trace = dtrace;
   a.seed = sp->seed;
   a.noise_free0 = sp->noise_free_filter0;
+  a.noise_mod = sp->noise_id_modulus;
   for (int i = 0; i < 6; ++i) {
     a.imu_noise[i] = sp->imu_noise_std[i];
     if (a.imu_noise[i] != 0.0) a.noise_on = 1;

@@ -62,6 +62,7 @@ struct KArgs {
   double cam_noise[7];
   int noise_on;
   int noise_free0;
+  int noise_mod;  // > 0: noise id = global id % noise_mod
 };
 
 // one FilterTraj row's worth of nominal state in the layout of x (include/eskf.h)
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(32 + 8 * F, 1) eskf_kernel(const __grid_consta
   double sig_om[3] = {0, 0, 0};
   double mse_last = 0.0, mse_sum = 0.0, n_upd = 0.0;
   const double* oap = nullptr;
-  const int64_t gid = gid0 + tid;
+  const int64_t gid = a.noise_mod > 0 ? (gid0 + tid) % a.noise_mod : gid0 + tid;  // id the noise is keyed by
   bool noisy = false;
   if (s_active) {
     const double* xg = a.x + (f0 + tid) * NX;

@@ -650,7 +650,7 @@ __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int l
   using L = Lay3<F>;
   const bool act = lane < c.nf;
   double* sx = c.smem + L::SX + lane;
-  const int64_t gid = c.gid0 + lane;
+  const int64_t gid = a.noise_mod > 0 ? (c.gid0 + lane) % a.noise_mod : c.gid0 + lane;  // id the noise is keyed by
   const bool noisy = a.noise_on && !(a.noise_free0 && gid == 0);
   const double* oap =
       a.om_acc ? (a.stream_per_filter ? a.om_acc + (c.f0 + lane) * a.T * 6 : a.om_acc + c.traj * a.T * 6) : nullptr;

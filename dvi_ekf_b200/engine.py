@@ -188,11 +188,13 @@ class BatchFilter:
     def run(self, dt, om_acc, n_prop, cam, notch, cam_ref=None, imu_ref=None, gt_dofs=(0, 0, 0, 0, 0, 20.0),
             n_traj: int = 1, filters_per_traj: Optional[int] = None, seed: int = 0, filter_id0: int = 0,
             imu_noise_std=None, cam_noise_std=None, noise_free_filter0: bool = True, want_stats: bool = True,
-            stats_on_device: bool = False, trace=None):
+            stats_on_device: bool = False, trace=None, noise_id_modulus: int = 0):
         """``Filter.run`` (Filter.py:144-185) for every filter, in one persistent kernel.
         Returns (stats [N,16], stats_sum [16]) (see include/eskf.h) or None.
         ``trace``: optional [N,T,26] float64 array (numpy for host streams, CUDA tensor for device streams) that
-        receives the nominal state after every IMU step, updated state at the update instants (FilterTraj rows)."""
+        receives the nominal state after every IMU step, updated state at the update instants (FilterTraj rows).
+        ``noise_id_modulus`` r > 0: the noise of global filter g is that of id g % r (common random numbers for
+        groups of r filters that differ only by their parameters)."""
         adt = _Arg(dt, None, name="dt")
         anp = _Arg(n_prop, None, dtype=np.int32, name="n_prop")
         T = adt.rows // n_traj
@@ -212,6 +214,7 @@ class BatchFilter:
         s.imu_noise_std = (C.c_double * 6)(*([0.0] * 6 if imu_noise_std is None else [float(v) for v in imu_noise_std]))
         s.cam_noise_std = (C.c_double * 7)(*([0.0] * 7 if cam_noise_std is None else [float(v) for v in cam_noise_std]))
         s.noise_free_filter0 = 1 if noise_free_filter0 else 0
+        s.noise_id_modulus = int(noise_id_modulus)
         if trace is not None:
             if tuple(trace.shape) != (self.n, T, 26):
                 raise ValueError(f"trace must have shape {(self.n, T, 26)}")

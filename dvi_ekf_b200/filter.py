@@ -320,6 +320,66 @@ class Simulator:
         self.x0 = State.from_vector(self.streams.x0)
         self._cov0 = cfg.cov0_matrix
 
+    # ---- batched tuner (Simulator.optimise, Simulator.py:163-245) -------------------------
+    OPTIM_BOUNDS = ((0, 10), (0, 10), (0, 10), (0, np.deg2rad(5)), (0, np.deg2rad(5)), (0, np.deg2rad(5)), (0, np.deg2rad(5)),
+                    (0, 0.2), (0, 0.2), (0, 0.2), (0, np.deg2rad(10)), (0, np.deg2rad(10)), (0, np.deg2rad(10)),
+                    (0, np.deg2rad(1)))  # random walks p(3) r(3) notch'' | measurement p_cam(3) r_cam(3) notch
+
+    def evaluate_candidates(self, X, runs_per_candidate: Optional[int] = None, metric: str = "dof"):
+        """Objective of ``Simulator.optimise`` for a whole POPULATION in one launch.  ``X`` is [M,14]: the optimisation
+        variables of the reference (random-walk std of the 6 DOFs and of the notch acceleration, measurement std of the
+        camera position, orientation and notch) -- unlike the reference's setter (Simulator.py:76-86, which keeps only
+        ``val[7:8]`` and never refreshes the variances) all 14 take effect.  Every candidate runs ``runs_per_candidate``
+        Monte-Carlo filters (run 0 of each candidate is noise free); returns the mean DOF MSE (``metric="dof"``,
+        Filter.calculate_dof_metric) or the mean update MSE (``"update"``) per candidate, [M]."""
+        X = np.atleast_2d(np.asarray(X, dtype=float))
+        if X.shape[1] != 14:
+            raise ValueError("candidates must have 14 columns: rw_std (7), meas_std (7)")
+        cfg, s, b = self.config, self.streams, self.config.batch
+        m, r = len(X), int(runs_per_candidate or self.num_kf_runs)
+        n = m * r
+        Qd = np.zeros((n, 13))
+        Qd[:, 6:13] = np.repeat(np.square(X[:, 0:7]), r, 0)
+        Rd = np.repeat(np.square(X[:, 7:14]), r, 0)
+        x0 = np.repeat(s.x0[None], n, 0)
+        for i in range(n):
+            if i % r:  # the same perturbed initial conditions and noise seeds for every candidate (common random numbers)
+                rng = np.random.default_rng([b.seed, i % r])
+                x0[i, 10:13] += rng.normal(0.0, np.deg2rad(b.dof_ic_std_deg), 3)
+                x0[i, 13:16] += rng.normal(0.0, b.dof_ic_std_cm, 3)
+        imu_std = np.hstack((cfg.imu.stdev_omega, cfg.imu.stdev_accel)) if b.imu_noise else None
+        cam_std = np.array(cfg.meas_noise_std) if b.cam_noise else None
+        with BatchFilter(n, scope_length=cfg.model.length, cam_angle_rad=cfg.model.angle, frozen_dofs=cfg.frozen_dofs,
+                         zero_frozen_dofs=not self.legacy_golden, device=self.device) as bf:
+            bf.set_noise(Qd, Rd, self.kf.stdev_nom[None].copy())
+            bf.set_state(x0, self._cov0[None], s.u0[None], None)
+            # noise keyed by the run id INSIDE the candidate (noise_id_modulus = r): every candidate sees the same
+            # r noise realisations, so candidates differ only by their parameters
+            st, _ = bf.run(s.dt, s.om_acc, s.n_prop, s.cam, s.notch, cam_ref=s.cam_ref, imu_ref=s.imu_ref,
+                           gt_dofs=cfg.gt_imu_dofs, seed=b.seed, imu_noise_std=imu_std, cam_noise_std=cam_std,
+                           noise_free_filter0=True, noise_id_modulus=r)
+        col = 6 if metric == "dof" else 8
+        vals = st[:, col].reshape(m, r)
+        if metric != "dof":
+            vals = vals / max(1, len(s.n_prop))
+        return vals.mean(axis=1)
+
+    def optimise(self, maxiter: int = 1, popsize: int = 1, runs_per_candidate: Optional[int] = None, seed: Optional[int] = None,
+                 metric: str = "dof"):
+        """``Simulator.optimise`` (Simulator.py:163-245): differential evolution over the 14 noise parameters, with the
+        objective of a whole generation evaluated by ONE batched launch (scipy ``vectorized=True``,
+        ``updating="deferred"``).  Returns the scipy result; the best parameters become ``optim_std``."""
+        from scipy.optimize import differential_evolution
+
+        def fun(x):  # x: (14, S) for a population of S members
+            return self.evaluate_candidates(np.asarray(x).T, runs_per_candidate, metric)
+
+        ret = differential_evolution(fun, self.OPTIM_BOUNDS, strategy="best1bin", maxiter=maxiter, popsize=popsize, seed=seed,
+                                     vectorized=True, updating="deferred", polish=False)
+        self._optim_std = list(ret.x)
+        self._dof_mse = float(ret.fun)
+        return ret
+
     def run_once(self) -> None:
         self.kf.run(self.camera, 0, "KF run")
         self.mse_best = self.kf.mse

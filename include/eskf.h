@@ -80,7 +80,8 @@ typedef struct {
   double imu_noise_std[6];  /* added to om(3), acc(3) of every IMU sample */
   double cam_noise_std[7];  /* added to camera position(3), as small rotation(3), notch(1) */
   int32_t noise_free_filter0; /* global filter 0 stays noise free (= the oracle run) */
-  int32_t reserved;
+  int32_t noise_id_modulus;   /* r > 0: filter g draws the noise of id g % r (common random numbers across parameter
+                               * candidates that each own r consecutive filters); 0: every filter its own noise */
   /* trace mode (nullable, in `mem` space): [N,T,26] nominal state after every IMU step, the row of the last step
    * of an epoch holding the UPDATED state -- the rows FilterTraj keeps (FilterTraj.py:34-69, Filter.py:229,382).
    * 208 B per filter-step: a diagnostic / export mode, HBM bound, not the production path. */

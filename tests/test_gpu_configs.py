@@ -133,3 +133,28 @@ def test_trace_mode_rows_between_updates(golden):
         kf.update(sc.cam_meas[e, :3], sc.cam_meas[e, 3:], sc.notch_meas[e])
         worst = max(worst, state_err(trace[1, k - 1], kf.get_vectors()[0]))
     assert worst < 1e-9, worst
+
+
+def test_batched_tuner_population_in_one_launch():
+    """the objective of Simulator.optimise for a whole population of (rw_std, meas_std) candidates in
+    one launch equals evaluating the candidates one by one, the candidates share their noise realisations, and one
+    generation of differential evolution runs on top of it."""
+    import os
+
+    from dvi_ekf_b200 import Config, Simulator
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = Config(os.path.join(root, "config.yaml"))
+    cfg.frozen_dofs = [0, 0, 0, 0, 0, 0]  # let the filter estimate the DOFs: the DOF MSE then depends on the tuning
+    sim = Simulator(cfg)
+    base = np.array([*cfg.process_noise_rw_std, *cfg.meas_noise_std], dtype=float)
+    X = np.array([base, base * 3.0, base * 0.3, base * np.linspace(0.5, 2.0, 14)])
+    f_all = sim.evaluate_candidates(X, runs_per_candidate=6)
+    assert f_all.shape == (4,) and np.all(np.isfinite(f_all)) and np.all(f_all >= 0)
+    f_one = np.array([sim.evaluate_candidates(X[j : j + 1], runs_per_candidate=6)[0] for j in range(4)])
+    assert np.array_equal(f_all, f_one)  # common random numbers: a candidate's score does not depend on its neighbours
+    assert len(set(np.round(f_all, 14))) > 1  # the parameters matter
+    ret = sim.optimise(maxiter=1, popsize=1, runs_per_candidate=3, seed=1)
+    assert ret.x.shape == (14,) and np.isfinite(ret.fun)
+    assert all(lo <= v <= hi for v, (lo, hi) in zip(ret.x, sim.OPTIM_BOUNDS))
+    assert ret.fun <= sim.evaluate_candidates(np.array([ret.x]), runs_per_candidate=3)[0] + 1e-12
