@@ -19,7 +19,7 @@ NSTAT = 16
 EXPORTS = (
     "eskf_create", "eskf_destroy", "eskf_set_state", "eskf_set_noise", "eskf_propagate", "eskf_update",
     "eskf_run", "eskf_get_state", "eskf_sync", "eskf_launch_count", "eskf_set_tuning", "eskf_last_error",
-    "eskf_version", "eskf_fp64_peak", "eskf_set_variant", "eskf_noise_dump",
+    "eskf_version", "eskf_fp64_peak", "eskf_set_variant", "eskf_noise_dump", "eskf_prepass", "eskf_prepass_last_error",
 )
 
 
@@ -57,6 +57,26 @@ class EskfStreams(C.Structure):
     ]
 
 
+class EskfPrepassIn(C.Structure):
+    _fields_ = [
+        ("n_frames", C.c_int64),
+        ("interframe_vals", C.c_int32),
+        ("euler_mode", C.c_int32),
+        ("scale", C.c_double),
+        ("gt_dofs", C.c_double * 6),
+        ("ic_dofs", C.c_double * 6),
+        ("t", C.c_void_p),
+        ("xyz", C.c_void_p),
+        ("q_xyzw", C.c_void_p),
+        ("notch3", C.c_void_p),
+    ]
+
+
+class EskfPrepassOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("x0", "u0", "dt", "om_acc", "t_imu", "n_prop", "cam", "notch", "cam_ref", "imu_ref",
+                                          "imu_ref_rows")]
+
+
 class EskfError(RuntimeError):
     pass
 
@@ -91,10 +111,13 @@ def load():
     lib.eskf_set_variant.argtypes = [vp, i32]
     lib.eskf_fp64_peak.argtypes = [i32, vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.eskf_noise_dump.argtypes = [i32, vp, C.c_uint64, i64, i64, i64, i64, i32, vp, i32]
+    lib.eskf_prepass.argtypes = [i32, vp, C.POINTER(EskfModel), C.POINTER(EskfPrepassIn), C.POINTER(EskfPrepassOut),
+                                 C.POINTER(C.c_int64)]
+    lib.eskf_prepass_last_error.restype = C.c_char_p
     lib.eskf_last_error.restype = C.c_char_p
     lib.eskf_version.restype = C.c_char_p
     for name in EXPORTS:
-        if name not in ("eskf_launch_count", "eskf_last_error", "eskf_version"):
+        if name not in ("eskf_launch_count", "eskf_last_error", "eskf_version", "eskf_prepass_last_error"):
             getattr(lib, name).restype = i32
     _lib = lib
     return lib

@@ -69,6 +69,9 @@ def build_cuda(force: bool = False, verbose: bool = False, defines=(), suffix: s
         obj = os.path.join(OBJ, f"eskf_launch3_f{f}.o")
         src = os.path.join(CSRC, "eskf_launch3.cu")
         jobs.append((obj, [src] + headers, [_nvcc(), *NVCC_FLAGS, *extra, f"-DESKF_F={f}", "-c", src, "-o", obj]))
+    pp_obj = os.path.join(OBJ, "eskf_prepass.o")
+    pp_src = os.path.join(CSRC, "eskf_prepass.cu")
+    jobs.append((pp_obj, [pp_src] + headers, [_nvcc(), *NVCC_FLAGS, *extra, "-c", pp_src, "-o", pp_obj]))
     api_obj = os.path.join(OBJ, "eskf_api.o")
     api_src = os.path.join(CSRC, "eskf_api.cu")
     jobs.append((api_obj, [api_src] + headers, [_nvcc(), *NVCC_FLAGS, *extra, "-c", api_src, "-o", api_obj]))

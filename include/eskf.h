@@ -144,6 +144,40 @@ enum { ESKF_NOISE_IMU = 1, ESKF_NOISE_CAM = 2 };
 int eskf_noise_dump(int device, void* cuda_stream, uint64_t seed, int64_t filter_id0, int64_t n_filters, int64_t step0,
                     int64_t n_steps, int kind, double* out, int mem);
 
+/* GPU pre-pass == Simulator.__init__ / Camera / Interpolator / Imu.eval_expr_single (Simulator.py:30-68,
+ * Camera.py:84-118,158-170,299-347, Interpolator.py:25-88, Imu.py:141-226, tools/utils.py:54-75): from one camera
+ * trajectory to the streams eskf_run consumes.  Inputs are HOST arrays, outputs DEVICE buffers owned by the caller with
+ * capacity T_max = (n_frames - 1) * interframe_vals steps and E = n_frames - 1 epochs; the number of IMU steps actually
+ * produced (epoch membership is decided by t_interp <= t_frame, quirk Q14) is returned in *n_steps_out. */
+typedef struct {
+  int64_t n_frames;
+  int32_t interframe_vals;  /* config.yaml imu.interframe_vals */
+  int32_t euler_mode;       /* 0: extrinsic xyz (HEAD); 1: zyx reversed (the revision that wrote the golden files) */
+  double scale;             /* camera.scale (VisualTrajectory.py:99-108) */
+  double gt_dofs[6];        /* config.gt_imu_dofs: probe used to synthesise the IMU */
+  double ic_dofs[6];        /* config.ic_imu_dofs: DOFs of the initial state */
+  const double* t;          /* [n]   frame stamps */
+  const double* xyz;        /* [n,3] unscaled positions */
+  const double* q_xyzw;     /* [n,4] raw quaternions */
+  const double* notch3;     /* [n,3] notch angle, rate, acceleration, or NULL (with_notch: false) */
+} eskf_prepass_in_t;
+typedef struct {
+  double* x0;               /* [26]       initial nominal state */
+  double* u0;               /* [6]        first IMU sample (Filter.py:63,78-79) */
+  double* dt;               /* [T_max] */
+  double* om_acc;           /* [T_max,6] */
+  double* t_imu;            /* [T_max]    nullable */
+  int32_t* n_prop;          /* [E] */
+  double* cam;              /* [E,7] */
+  double* notch;            /* [E] */
+  double* cam_ref;          /* [E,6] */
+  double* imu_ref;          /* [E,6] */
+  double* imu_ref_rows;     /* [T_max,14] ImuRefTraj rows (ImuRefTraj.py:18-55), nullable */
+} eskf_prepass_out_t;
+int eskf_prepass(int device, void* cuda_stream, const eskf_model_t* model, const eskf_prepass_in_t* in,
+                 const eskf_prepass_out_t* out, int64_t* n_steps_out);
+const char* eskf_prepass_last_error(void);
+
 /* Measurement aid (no reference counterpart): sustained FP64 FMA throughput of the device in
  * TFLOP/s (best of `repeats` launches of a pure DFMA kernel) -- the roofline denominator. */
 int eskf_fp64_peak(int device, void* cuda_stream, int repeats, double* tflops_out, double* ms_out);
