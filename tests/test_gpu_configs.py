@@ -158,3 +158,31 @@ def test_batched_tuner_population_in_one_launch():
     assert ret.x.shape == (14,) and np.isfinite(ret.fun)
     assert all(lo <= v <= hi for v, (lo, hi) in zip(ret.x, sim.OPTIM_BOUNDS))
     assert ret.fun <= sim.evaluate_candidates(np.array([ret.x]), runs_per_candidate=3)[0] + 1e-12
+
+
+@pytest.mark.parametrize("variant", [3, 1])
+def test_ragged_and_empty_epochs(golden, variant):
+    """epochs with 0, 1, 2 and many IMU samples in one launch (the record pipeline, the mid-step waits and the barriers
+    around the update must hold for every epoch length), against the oracle driven by the same n_prop."""
+    from dvi_ekf_b200 import BatchFilter
+
+    sc = mandala_scenario(golden, n_frames=8, ifv=10)  # 70 samples, 7 camera frames
+    n_prop = np.array([3, 0, 1, 17, 2, 0, 47], dtype=np.int32)
+    assert n_prop.sum() == len(sc.dt)
+    with BatchFilter(9, variant=variant, **model_kwargs(sc.cfg)) as bf:
+        bf.set_noise(sc.Qd[None], sc.Rd[None], sc.sig_om[None])
+        bf.set_state(sc.x0[None], sc.P0[None], sc.u0[None], None)
+        st, sm = bf.run(sc.dt, sc.om_acc, n_prop, sc.cam_meas, sc.notch_meas)
+        xg, Pg, ug, Rg, status = bf.get_state()
+    kf = sc.new_oracle()
+    k = 0
+    for e in range(len(n_prop)):
+        for _ in range(n_prop[e]):
+            kf.propagate(sc.dt[k], sc.om_acc[k, :3], sc.om_acc[k, 3:])
+            k += 1
+        kf.update(sc.cam_meas[e, :3], sc.cam_meas[e, 3:], sc.notch_meas[e])
+    xr, Pr, ur, Rr = kf.get_vectors()
+    assert np.all(status == 0) and np.allclose(st[:, 9], len(n_prop))
+    for i in (0, 8):
+        assert state_err(xg[i], xr) < 1e-8 and cov_err(Pg[i], Pr, sc.Rd) < 1e-8
+        assert np.abs(ug[i] - ur).max() < 1e-12 and np.abs(Rg[i] - Rr).max() < 1e-9
