@@ -106,6 +106,18 @@ def cpu_sample(procs, filters_per_proc, n_epochs):
     return work, busy, wall
 
 
+def workload_config(n, T, E, world, fpc):
+    """`config` of the JSON line: the same for both arms (the reference arm times a bounded sample of it)."""
+    return {
+        "workload": f"config2: {n} Monte-Carlo filters per GPU (Philox noise seeds, DOF IC perturbation) on the default "
+                    f"simulated trajectory mandala0_mono, {N_FRAMES} frames x {IFV} IMU samples "
+                    f"({T} propagates + {E} updates per filter per pass)",
+        "filters_per_gpu": n, "filter_steps_per_pass": int(n) * T * world,
+        "l2": "flushed between timed iterations (256 MiB memset)", "filters_per_cta": fpc or "auto",
+        "parallelism": f"filters sharded over {world} GPU(s)",
+    }
+
+
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -126,8 +138,7 @@ def run_reference_arm(a):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config2: Monte-Carlo filters on the default simulated trajectory (mandala0_mono, "
-                               "140 frames x 10 IMU samples), bounded sample", "sample": sample},
+        "config": dict(workload_config(a.filters, (N_FRAMES - 1) * IFV, N_FRAMES - 1, 1, a.fpc), sample=sample),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -386,13 +397,7 @@ def run_ours(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {
-                "workload": f"config2: {n} Monte-Carlo filters per GPU (Philox noise seeds, DOF IC perturbation) on the default "
-                            f"simulated trajectory mandala0_mono, {N_FRAMES} frames x {IFV} IMU samples "
-                            f"({T} propagates + {E} updates per filter per pass)",
-                "filters_per_gpu": n, "filter_steps_per_pass": int(n) * T * world, "l2": "flushed between timed iterations "
-                "(256 MiB memset)", "filters_per_cta": a.fpc or "auto", "parallelism": f"filters sharded over {world} GPU(s)",
-            },
+            "config": workload_config(n, T, E, world, a.fpc),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_t},
