@@ -740,75 +740,70 @@ __device__ __forceinline__ double rcp_nr(double x) {
   return r;
 }
 
-// inv(S) by the eight lanes of a filter: lane c < 7 owns column c of [S | I].  LU with partial pivoting
-// + back substitution, the same operations in the same order as eskf::inv7 (the host-checkable
-// restatement of np.linalg.inv -> LAPACK gesv, Filter.py:357); multipliers and U entries travel by
-// width-8 shuffles.  Reads S from / writes inv(S) to the u3 record.  False for an exactly singular or
-// non-finite S (the reference's LinAlgError branch, Filter.py:358-361).
+// inv(S) (np.linalg.inv, Filter.py:357) by the eight lanes of a filter: in-place Gauss-Jordan elimination with
+// partial pivoting, lane r < 7 owning ROW r of S.  The pivot row of column k is chosen among the unused rows by a
+// three-stage shuffle reduction (largest |entry|, as LAPACK's partial pivoting does) and is never moved: its lane
+// simply plays row k.  Every step is the same code whatever k -- the rows are kept rotated so that the pivot column
+// is element 0 and the finished inverse column goes to element 6 -- so the seven steps are a ROLLED loop of ~80
+// instructions (the column-owned LU it replaces was 1,500 unrolled instructions and 4.6 k cycles of dependent
+// shuffles per update).  Reads S from / writes inv(S) to the u3 record.  False for a singular or non-finite S
+// (the reference's LinAlgError branch, Filter.py:358-361).
 template <int QS>
 __device__ __forceinline__ bool inv7_group3(double* rec, int g) {
   const unsigned FULL = 0xffffffffu;
-  const int c = (g < 7) ? g : 6;
-  double a[7], b[7];
+  const int r = (g < 7) ? g : 6;  // lane 7 shadows row 6 and never becomes a pivot
+  double a[7];
 #pragma unroll
-  for (int i = 0; i < 7; ++i) {
-    a[i] = u3_get<QS>(rec, U3_S + 7 * i + c);
-    b[i] = (i == c) ? 1.0 : 0.0;
-  }
+  for (int j = 0; j < 7; ++j) a[j] = u3_get<QS>(rec, U3_S + 7 * r + j);
+  bool used = (g == 7);
   bool ok = true;
-  double rpiv = 0.0;
-#pragma unroll
+  int myk = 0;         // the row of inv(S) this lane ends up holding
+  unsigned plist = 0;  // 3 bits per step: lane of the pivot row of column k
+#pragma unroll 1
   for (int k = 0; k < 7; ++k) {
-    int piv = k;
-    double best = fabs(a[k]);
+    // pivot search over the unused rows
+    double best = used ? -1.0 : fabs(a[0]);
+    int piv = g;
 #pragma unroll
-    for (int i = k + 1; i < 7; ++i) {
-      const double v = fabs(a[i]);
-      if (v > best) {
-        best = v;
-        piv = i;
+    for (int o = 1; o < 8; o <<= 1) {
+      const double ob = __shfl_xor_sync(FULL, best, o, 8);
+      const int op = __shfl_xor_sync(FULL, piv, o, 8);
+      if (ob > best || (ob == best && op < piv)) {
+        best = ob;
+        piv = op;
       }
     }
-    piv = __shfl_sync(FULL, piv, k, 8);
-    best = __shfl_sync(FULL, best, k, 8);
-    ok = ok && (best != 0.0);
-#pragma unroll
-    for (int i = k + 1; i < 7; ++i) {
-      if (piv == i) {
-        double t = a[k];
-        a[k] = a[i];
-        a[i] = t;
-        t = b[k];
-        b[k] = b[i];
-        b[i] = t;
-      }
+    ok = ok && (best > 0.0);
+    plist |= (unsigned)piv << (3 * k);
+    const bool mine = (piv == g);
+    if (mine) {
+      used = true;
+      myk = k;
     }
-    const double rp = rcp_nr(a[k]);
-    if (k == c) rpiv = rp;  // 1 / U(k, k), needed again by the back substitution
+    // scaled pivot row (column 0 replaced by 1 / pivot), broadcast from its lane
+    const double rp = rcp_nr(a[0]);
+    double pr[7];
 #pragma unroll
-    for (int i = k + 1; i < 7; ++i) {
-      const double l = __shfl_sync(FULL, a[i] * rp, k, 8);
-      a[i] -= l * a[k];
-      b[i] -= l * b[k];
+    for (int j = 1; j < 7; ++j) pr[j - 1] = __shfl_sync(FULL, a[j] * rp, piv, 8);
+    pr[6] = __shfl_sync(FULL, rp, piv, 8);
+    const double f = a[0];
+    if (mine) {
+#pragma unroll
+      for (int j = 0; j < 7; ++j) a[j] = pr[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) a[j] = a[j + 1] - f * pr[j];
+      a[6] = -f * pr[6];
     }
   }
-#pragma unroll
-  for (int i = 6; i >= 0; --i) {
-    double v = b[i];
-#pragma unroll
-    for (int k = i + 1; k < 7; ++k) {
-      const double uik = __shfl_sync(FULL, a[i], k, 8);
-      v -= uik * b[k];
-    }
-    b[i] = v * __shfl_sync(FULL, rpiv, i, 8);
-  }
+  // lane p_k holds row k of inv(P S) = inv(S) P^T (P: the row permutation of the pivoting): inv(S)(k, p_j) = a[j]
   double chk = 0.0;
 #pragma unroll
-  for (int i = 0; i < 7; ++i) chk += b[i] * 0.0;  // NaN / inf detector
+  for (int j = 0; j < 7; ++j) chk += a[j] * 0.0;  // NaN / inf detector
   ok = ok && (chk == 0.0);
   if (g < 7) {
 #pragma unroll
-    for (int i = 0; i < 7; ++i) u3_at<QS>(rec, U3_SINV + 7 * i + c) = b[i];
+    for (int j = 0; j < 7; ++j) u3_at<QS>(rec, U3_SINV + 7 * myk + (int)((plist >> (3 * j)) & 7u)) = a[j];
   }
   const unsigned bal = __ballot_sync(FULL, ok);
   const unsigned lane = threadIdx.x & 31u;
