@@ -119,3 +119,29 @@ def test_noise_generator_statistics():
     assert not np.array_equal(z[:4, :4], noise_samples(99, 0, 4, 0, 4, NOISE_CAM))
     assert not np.array_equal(z[:4, :4], noise_samples(100, 0, 4, 0, 4, NOISE_IMU))
     assert np.array_equal(z[3:7, 10:14], noise_samples(99, 3, 4, 10, 4, NOISE_IMU))
+
+
+def test_bench_sized_run_is_deterministic_and_shape_independent(golden):
+    """4096 noisy filters over the whole trajectory (the launch bench.py times), three times and with two CTA shapes: every
+    state and covariance bit-identical -- a data race in the role pipelines (mbarrier record slots, named barriers, the
+    shared exchange records) would show up as run-to-run differences.  Also P stays symmetric and positive on the diagonal."""
+    from dvi_ekf_b200 import BatchFilter
+
+    sc = mandala_scenario(golden, n_frames=140, ifv=10)
+    n = 4096
+    outs = []
+    for fpc in (28, 28, 16, 28):
+        with BatchFilter(n, **model_kwargs(sc.cfg)) as bf:
+            bf.set_tuning(fpc)
+            bf.set_noise(sc.Qd[None], sc.Rd[None], sc.sig_om[None])
+            bf.set_state(sc.x0[None], sc.P0[None], sc.u0[None], None)
+            bf.run(sc.dt, sc.om_acc, sc.n_prop, sc.cam_meas, sc.notch_meas, seed=SEED, imu_noise_std=IMU_STD, cam_noise_std=CAM_STD)
+            outs.append(bf.get_state())
+    for o in outs[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(o, outs[0]))
+    x, P, u, Ro, st = outs[0]
+    assert np.all(st == 0) and np.all(np.isfinite(x)) and np.all(np.isfinite(P))
+    asym = np.abs(P - np.swapaxes(P, 1, 2)).max(axis=(1, 2)) / np.abs(P).max(axis=(1, 2))
+    assert asym.max() < 1e-9
+    assert np.all(np.diagonal(P, axis1=1, axis2=2) > 0)
+    assert np.abs(np.linalg.norm(x[:, 6:10], axis=1) - 1).max() < 1e-12 and np.abs(np.linalg.norm(x[:, 22:26], axis=1) - 1).max() < 1e-12
