@@ -18,7 +18,7 @@ from . import rotations as rot
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "trajs.npz")
 
 
-def load_trajectory(name_or_path: str, max_vals: Optional[int] = None, start_frame=None):
+def load_trajectory(name_or_path: str, max_vals: Optional[int] = None, start_frame=None, with_start_index: bool = False):
     """Returns (t, xyz, q_xyzw) from a csv with header ``t,x,y,z,qx,qy,qz,qw`` (tools/files.py:19-28), a
     headerless space-separated txt, or one of the trajectories shipped in data/trajs.npz (by name)."""
     if os.path.exists(name_or_path):
@@ -32,19 +32,40 @@ def load_trajectory(name_or_path: str, max_vals: Optional[int] = None, start_fra
             if key not in z:
                 raise FileNotFoundError(f"{name_or_path}: no such file and no packaged trajectory {key!r}")
             a = z[key]
+    i0 = 0
     if start_frame:
         i0 = int(np.argwhere(a[:, 0] == start_frame).item())
         a = a[i0:]
     if max_vals:
         a = a[:max_vals]
-    return a[:, 0].copy(), a[:, 1:4].copy(), a[:, 4:8].copy()
+    out = (a[:, 0].copy(), a[:, 1:4].copy(), a[:, 4:8].copy())
+    return out + (i0,) if with_start_index else out
+
+
+def load_notch(name_or_path: str, max_vals: Optional[int] = None, start_index: int = 0):
+    """Notch trajectory [n,3] = angle, rate, acceleration per camera frame (config ``notch_traj_name``,
+    VisualTrajectory.py:110-118).  The shipped ``notch90.csv`` is COMMA separated; the reference's loader splits on white
+    space and appends to ``None`` (``with_notch: true`` cannot run at HEAD) -- read here the way the file
+    is written, from a path or from the packaged data/trajs.npz."""
+    if os.path.exists(name_or_path):
+        with open(name_or_path, "r") as f:
+            a = np.array([[float(v) for v in line.strip().split(",")[:3]] for line in f if line.strip()])
+    else:
+        key = "notch_" + os.path.splitext(os.path.basename(name_or_path))[0]
+        with np.load(_DATA) as z:
+            if key not in z:
+                raise FileNotFoundError(f"{name_or_path}: no such file and no packaged notch trajectory {key!r}")
+            a = z[key]
+    a = a[start_index:]
+    return (a[:max_vals] if max_vals else a).copy()
 
 
 class Camera:
     """``Camera`` (Camera.py:41-118): t, p (3,n), raw + normalised quaternions, R, and the derived
     v / acc / om / alp obtained with np.gradient (Camera.py:158-170)."""
 
-    def __init__(self, t, xyz, q_xyzw, scale=1.0, euler_mode="xyz", notch=None, _derived=None, interframe_vals=0):
+    def __init__(self, t, xyz, q_xyzw, scale=1.0, euler_mode="xyz", notch=None, _derived=None, interframe_vals=0,
+                 _is_rotated=False):
         self.t = np.asarray(t, dtype=float)
         self.p = (np.asarray(xyz, dtype=float) * scale).T.copy() if _derived is None else np.asarray(xyz, dtype=float)
         self.q_raw = np.asarray(q_xyzw, dtype=float)
@@ -65,6 +86,23 @@ class Camera:
             self.alp = np.gradient(self.om, self.dt, axis=-1)
         else:
             self.v, self.acc, self.om, self.alp = _derived
+        # Camera.py:131-134: with a notch trajectory the filter's IMU source and error reference is the ROTATED camera
+        self.is_rotated = False
+        self.rotated: Optional["Camera"] = None
+        if self.with_notch and _derived is None and not _is_rotated:
+            self.rotated = self.gen_rotated()
+
+    def gen_rotated(self) -> "Camera":
+        """``Camera.gen_rotated`` (Camera.py:172-208): same positions, quaternions ``notch_quat * real_quat`` with
+        ``notch_quat = Quaternion([0, 0, ang_notch], euler="xyz")``; the product is re-normalised with w >= 0
+        (Quaternion.__mul__, quirk Q10).  The rotated camera re-derives om / alp from ITS Euler angles and carries the
+        same notch arrays."""
+        h = 0.5 * self.notch3[:, 0]
+        nq = np.stack((np.zeros_like(h), np.zeros_like(h), np.sin(h), np.cos(h)), -1)
+        r = Camera(self.t, self.p.T, rot.normalise(rot.multiply(nq, self.quats)), scale=1.0, euler_mode=self.euler_mode,
+                   notch=self.notch3, _is_rotated=True)
+        r.is_rotated = True
+        return r
 
     @property
     def flag_interpolated(self):
@@ -136,6 +174,9 @@ def build_streams(cam: Camera, interframe_vals: int, length: float, angle: float
     """Host pre-pass of Simulator.__init__ / Filter.__init__ / Filter.propagate_imu: initial state
     (tools/utils.py:54-75), synthetic IMU samples at every interpolated instant (Imu.py:141-226) and the
     per-epoch membership decided by ``t_interp <= t_frame`` (Camera.py:299-301,320-347; quirk Q14)."""
+    meas = cam  # Filter.run is handed the un-rotated camera: its frames are the measurements (Filter.py:144-185)
+    if cam.rotated is not None:
+        cam = cam.rotated  # IMU source (Imu.py:87-90), initial state (tools/utils.py:63-75), error reference (Filter.py:398)
     ci = cam.interpolate(interframe_vals)
     gt = np.asarray(gt_dofs, dtype=float)
     # ground-truth probe at every interpolated instant (notch joint from the notch trajectory)
@@ -163,5 +204,5 @@ def build_streams(cam: Camera, interframe_vals: int, length: float, angle: float
     ends = idx[1:]
     cam_ref = np.hstack((cam.p.T[1:], cam.r_deg[1:]))
     return Streams(x0=x0, u0=np.hstack((om[0], acc[0])), dt=dt, om_acc=np.hstack((om[sel], acc[sel])), t_imu=ci.t[sel],
-                   n_prop=n_prop, cam=np.hstack((cam.p.T[1:], cam.q_raw[1:])), notch=cam.notch3[1:, 0].copy(),
+                   n_prop=n_prop, cam=np.hstack((meas.p.T[1:], meas.q_raw[1:])), notch=meas.notch3[1:, 0].copy(),
                    cam_ref=cam_ref, imu_ref=ref_rows[ends][:, 4:10], imu_ref_rows=ref_rows[sel], t_cam=cam.t.copy())

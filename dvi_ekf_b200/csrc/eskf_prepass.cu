@@ -8,6 +8,8 @@
 //   synthetic IMU ............... dvi_ekf/models/Imu.py:141-226, dvi_ekf/kinematics/equations.py:8-41,54-69
 //   epoch membership ............ dvi_ekf/models/Camera.py:299-301,320-347 (t_interp <= t_frame, quirk Q14)
 //   initial state ............... dvi_ekf/tools/utils.py:54-75
+//   rotated camera (with_notch) . dvi_ekf/models/Camera.py:172-208 (IMU source, initial state and error reference; the
+//                                 measurements stay those of the un-rotated camera, Filter.py:144-185)
 // One thread per camera frame for the derived data, one thread per interpolated instant for the IMU synthesis.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -35,6 +37,7 @@ struct PP {
   // frame arrays (device)
   const double *t, *xyz, *q, *notch3;
   double *p, *qn, *ang, *rdeg, *v, *om, *acc, *alp;  // [n,3] / [n,4]
+  double* qsrc;  // [n,4] quaternion channel the Interpolator reads: the raw file columns, or the rotated camera's
   // per interpolated instant
   double *tn, *oa_all, *ref_all;  // [n_new], [n_new,6], [n_new,14]
   int64_t* idx;                   // [n] index of the last interpolated instant with t <= frame time
@@ -62,6 +65,21 @@ __global__ void pp_frames(PP a) {
   for (int j = 0; j < 3; ++j) a.p[3 * i + j] = a.xyz[3 * i + j] * a.scale;
   for (int j = 0; j < 4; ++j) q[j] = a.q[4 * i + j];
   quat_normalise(q);
+  if (a.with_notch) {
+    // Camera.gen_rotated (Camera.py:172-208): notch_quat * real_quat with notch_quat = Rz(ang_notch); the rotated camera is
+    // the IMU source, the initial state and the error reference; its quaternion columns are already normalised
+    double sh, ch, nq[4], qr[4];
+    sincos(0.5 * a.notch3[3 * i], &sh, &ch);
+    nq[0] = 0.0;
+    nq[1] = 0.0;
+    nq[2] = sh;
+    nq[3] = ch;
+    quat_mul(nq, q, qr);
+    for (int j = 0; j < 4; ++j) q[j] = qr[j];
+    for (int j = 0; j < 4; ++j) a.qsrc[4 * i + j] = q[j];
+  } else {
+    for (int j = 0; j < 4; ++j) a.qsrc[4 * i + j] = a.q[4 * i + j];
+  }
   for (int j = 0; j < 4; ++j) a.qn[4 * i + j] = q[j];
   quat_to_rot(q, R);
   euler_of(R, a.euler_mode, e);
@@ -130,7 +148,7 @@ __global__ void pp_samples(PP a) {
     alp[c] = interp1(x, a.t, k, a.n, a.alp, 3, c);
     if (a.with_notch) nt[c] = interp1(x, a.t, k, a.n, a.notch3, 3, c);
   }
-  for (int c = 0; c < 4; ++c) q[c] = interp1(x, a.t, k, a.n, a.q, 4, c);  // RAW components, re-normalised below
+  for (int c = 0; c < 4; ++c) q[c] = interp1(x, a.t, k, a.n, a.qsrc, 4, c);  // RAW components, re-normalised below
   quat_normalise(q);
   double R_WC[9];
   quat_to_rot(q, R_WC);
@@ -339,7 +357,7 @@ int eskf_prepass(int device, void* cuda_stream, const eskf_model_t* model, const
   a.xyz = dxyz;
   a.q = dq;
   a.notch3 = dn3;
-  PCK(dalloc((size_t)n * 25 * sizeof(double), (void**)&frame));  // p 3, qn 4, ang 3, rdeg 3, v 3, om 3, acc 3, alp 3
+  PCK(dalloc((size_t)n * 29 * sizeof(double), (void**)&frame));  // p 3, qn 4, ang 3, rdeg 3, v 3, om 3, acc 3, alp 3, qsrc 4
   a.p = frame;
   a.qn = frame + 3 * n;
   a.ang = frame + 7 * n;
@@ -348,6 +366,7 @@ int eskf_prepass(int device, void* cuda_stream, const eskf_model_t* model, const
   a.om = frame + 16 * n;
   a.acc = frame + 19 * n;
   a.alp = frame + 22 * n;
+  a.qsrc = frame + 25 * n;
   PCK(dalloc((size_t)n_new * 21 * sizeof(double), (void**)&samp));
   a.tn = samp;
   a.oa_all = samp + n_new;

@@ -14,7 +14,7 @@ from typing import List, Optional
 import numpy as np
 
 from . import rotations as rot
-from .camera import Camera, Streams, build_streams, load_trajectory
+from .camera import Camera, Streams, build_streams, load_notch, load_trajectory
 from .config import Config
 from .engine import BatchFilter
 from .probe import GT_IMU_DOFS
@@ -246,6 +246,7 @@ class Filter:
     # ---- metrics (Filter.py:397-455) -------------------------------------------------------
     def calculate_update_mse(self, i_cam, camera):
         kf = self.traj.rows[-1]
+        camera = camera.rotated if camera.rotated is not None else camera  # Filter.py:398
         cam_ref = np.hstack((camera.p[:, i_cam], camera.r_deg[i_cam]))
         s_cam = np.sum(np.square(cam_ref - kf[20:26]))
         s_imu = np.sum(np.square(kf[4:10] - self.imu.ref_rows[-1][4:10]))
@@ -309,12 +310,18 @@ class Simulator:
         self.kf.update_noise_matrices()
 
     def _update_config(self, cfg: Config) -> None:
-        t, xyz, q = load_trajectory(str(cfg.traj_fp), max_vals=cfg.max_vals, start_frame=cfg.camera.start_frame)
+        t, xyz, q, i0 = load_trajectory(str(cfg.traj_fp), max_vals=cfg.max_vals, start_frame=cfg.camera.start_frame,
+                                        with_start_index=True)
         mode = "zyx_legacy" if self.legacy_golden else "xyz"
-        self.camera = Camera(t, xyz, q, scale=cfg.camera.scale, euler_mode=mode)
+        # with_notch: true (unrunnable at the reference's HEAD, quirk Q12): the notch rows are cut like the
+        # camera rows (VisualTrajectory.py:66-70) and the camera generates its rotated twin (Camera.py:131-134)
+        notch = load_notch(str(cfg.notch_fp), max_vals=len(t), start_index=i0) if cfg.with_notch else None
+        if notch is not None and len(notch) != len(t):
+            raise ValueError(f"notch trajectory has {len(notch)} rows for {len(t)} camera frames")  # VisualTrajectory.py:70
+        self.camera = Camera(t, xyz, q, scale=cfg.camera.scale, euler_mode=mode, notch=notch)
         cfg.max_vals, cfg.min_t, cfg.max_t = self.camera.max_vals, self.camera.min_t, self.camera.max_t
         cfg.total_data_pts = (self.camera.max_vals - 1) * cfg.interframe_vals + 1
-        self.camera_interp = self.camera.interpolate(cfg.interframe_vals)
+        self.camera_interp = (self.camera.rotated or self.camera).interpolate(cfg.interframe_vals)  # Imu.create (Imu.py:87-90)
         self.streams: Streams = build_streams(self.camera, cfg.interframe_vals, cfg.model.length, cfg.model.angle,
                                               gt_dofs=cfg.gt_imu_dofs, ic_dofs=cfg.ic_imu_dofs)
         self.x0 = State.from_vector(self.streams.x0)

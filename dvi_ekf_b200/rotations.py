@@ -17,6 +17,16 @@ def normalise(q):
     return np.where(q[..., 3:4] < 0, -q, q)
 
 
+def multiply(a, b):
+    """Hamilton product a * b of xyzw quaternions (Quaternion.__mul__, Quaternion.py:170-183) WITHOUT the final
+    re-normalisation -- callers apply ``normalise`` like the reference's ``do_normalise=True``."""
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    aw, av, bw, bv = a[..., 3:4], a[..., :3], b[..., 3:4], b[..., :3]
+    w = aw * bw - np.sum(av * bv, axis=-1, keepdims=True)
+    v = aw * bv + bw * av + np.cross(av, bv)
+    return np.concatenate((v, w), axis=-1)
+
+
 def to_matrix(q):
     """Quaternion.rot (Quaternion.py:101-107) for unit quaternions; shape (...,3,3)."""
     q = np.asarray(q, dtype=float)

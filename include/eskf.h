@@ -159,7 +159,9 @@ typedef struct {
   const double* t;          /* [n]   frame stamps */
   const double* xyz;        /* [n,3] unscaled positions */
   const double* q_xyzw;     /* [n,4] raw quaternions */
-  const double* notch3;     /* [n,3] notch angle, rate, acceleration, or NULL (with_notch: false) */
+  const double* notch3;     /* [n,3] notch angle, rate, acceleration, or NULL (with_notch: false).  When given, the IMU
+                               samples, x0 and cam_ref come from the ROTATED camera (Camera.gen_rotated, Camera.py:172-208)
+                               and `cam` keeps the raw quaternions of the un-rotated one, as Filter.run sees them */
 } eskf_prepass_in_t;
 typedef struct {
   double* x0;               /* [26]       initial nominal state */

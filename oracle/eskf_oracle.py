@@ -446,6 +446,35 @@ def camera_interpolate(cam: CameraData, interframe_vals: int) -> CameraData:
     return CameraData(t_new, p, q_lin, quats, R, v, acc, om, alp, notch, interframe_vals)
 
 
+def load_notch_csv(path, max_vals=None, start_index=0):
+    """``VisualTraj.read_notch_from_file`` (VisualTrajectory.py:110-118) with the Q12 defect repaired the only way
+    the shipped file allows: ``data/trajs/notch90.csv`` holds ``notch,notch_d,notch_dd`` per line, COMMA separated
+    (HEAD splits on white space and appends to ``None``).  Rows are cut like the camera rows
+    (``_filter_values``, VisualTrajectory.py:69)."""
+    rows = []
+    with open(path, "r") as f:
+        for line in f:
+            line = line.strip()
+            if line:
+                rows.append([float(v) for v in line.split(",")[:3]])
+    a = np.array(rows)[start_index:]
+    return a[:max_vals] if max_vals else a
+
+
+def camera_gen_rotated(cam: CameraData, cfg: OracleConfig) -> CameraData:
+    """``Camera.gen_rotated`` (Camera.py:172-208): same positions, every quaternion pre-multiplied by the notch
+    rotation ``Quaternion([0, 0, ang_notch], euler="xyz") * real_quat`` (product re-normalised, w >= 0: Q10); the
+    rotated trajectory becomes a new ``Camera`` whose derived data are the gradients of ITS Euler angles, and it
+    carries the same notch arrays (Camera.py:204-206)."""
+    q_rot = np.array([quat_mul(quat_from_euler_xyz([0.0, 0.0, cam.notch[i, 0]]), cam.quats[i]) for i in range(len(cam.t))])
+    R = np.array([quat_to_matrix(q) for q in q_rot])
+    dt = cam.t[1] - cam.t[0]
+    ang = _euler_for_gradient(q_rot, cfg.euler_mode)
+    om = np.gradient(ang, dt, axis=-1)
+    alp = np.gradient(om, dt, axis=-1)
+    return CameraData(cam.t, cam.p, q_rot.copy(), q_rot, R, cam.v, cam.acc, om, alp, cam.notch)
+
+
 def _timestamp_index(ts, max_t):
     """Camera.py:299-301."""
     return max(i for i, t in enumerate(ts) if t <= max_t)
@@ -735,12 +764,18 @@ def imu_ref_row(t, p_C, R_WC, v_C, om_C, fw_gt):
     return np.array([t, *p, *v, *eul, q[3], q[0], q[1], q[2]])
 
 
-def build_streams(cam: CameraData, cfg: OracleConfig, probe: Probe):
+def build_streams(cam: CameraData, cfg: OracleConfig, probe: Probe, rotated: Optional[CameraData] = None):
     """Everything ``Simulator.__init__`` + ``Filter.__init__`` +
     ``Filter.propagate_imu`` derive from the camera before touching the
     filter state: initial state (tools/utils.py:54-75), first IMU sample
     (Imu.py:198-226), per-step dt / IMU samples (Filter.py:187-217) and the
-    per-epoch sample counts decided by float comparison (Camera.py:320-347)."""
+    per-epoch sample counts decided by float comparison (Camera.py:320-347).
+    With ``with_notch`` the IMU is synthesised from the ROTATED camera (``Imu.create``, Imu.py:87-90) and the initial
+    state comes from it too (tools/utils.py:63-75); the measurements handed to ``Filter.update`` stay those of the
+    un-rotated camera (``Filter.run`` is given ``camera``, Filter.py:144-185)."""
+    meas = cam
+    if rotated is not None:
+        cam = rotated
     cam_i = camera_interpolate(cam, cfg.interframe_vals)
     notch0 = cam.notch[0]
     fw0 = probe.fwkin([*GT_IMU_DOFS, notch0[0], 0.0], [0.0] * 6 + [notch0[1], 0.0], [0.0] * 6 + [notch0[2], 0.0])
@@ -765,8 +800,8 @@ def build_streams(cam: CameraData, cfg: OracleConfig, probe: Probe):
             old_ti = cam_i.t[k]
         n_prop.append(new_i - old_i)
         old_t = t
-    cam_meas = np.hstack((cam.p.T[1:], cam.q_raw[1:]))
-    notch_meas = cam.notch[1:, 0].copy()
+    cam_meas = np.hstack((meas.p.T[1:], meas.q_raw[1:]))
+    notch_meas = meas.notch[1:, 0].copy()
     return x0, np.hstack((om0, acc0)), np.array(dts), np.array(oas), np.array(n_prop), cam_meas, notch_meas, np.array(ref_rows)
 
 
@@ -775,11 +810,16 @@ def cam_euler_deg(cam: CameraData):
     return np.array([Rotation.from_quat(q).as_euler("xyz", degrees=True) for q in cam.quats])
 
 
-def run_reference_flow(t, xyz, q_xyzw, cfg: OracleConfig, keep_steps=False) -> RunResult:
-    """``main.py``: Config -> Simulator -> ``Filter.run`` (Filter.py:144-185)."""
+def run_reference_flow(t, xyz, q_xyzw, cfg: OracleConfig, keep_steps=False, notch=None) -> RunResult:
+    """``main.py``: Config -> Simulator -> ``Filter.run`` (Filter.py:144-185).  ``notch`` [n,3] = the rows of the notch
+    trajectory file: the ``with_notch: true`` flow (rotated camera as IMU source and as the error reference,
+    Filter.py:398)."""
     probe = Probe(cfg.length, cfg.angle)
-    cam = camera_from_arrays(t, xyz, q_xyzw, cfg)
-    x0, u0, dts, oas, n_prop, cam_meas, notch_meas, ref_rows = build_streams(cam, cfg, probe)
+    cam = camera_from_arrays(t, xyz, q_xyzw, cfg, notch=notch)
+    rotated = camera_gen_rotated(cam, cfg) if notch is not None else None
+    x0, u0, dts, oas, n_prop, cam_meas, notch_meas, ref_rows = build_streams(cam, cfg, probe, rotated)
+    if rotated is not None:
+        cam = rotated  # ``cam_reference = camera.rotated if camera.rotated else camera`` (Filter.py:398)
     kf = OracleFilter(cfg, x0, cfg.cov0_matrix, u0[:3], u0[3:], probe)
     res = RunResult(
         kf_rows=None, imu_ref_rows=ref_rows, dt=dts, om_acc=oas, n_prop=n_prop, cam_meas=cam_meas,

@@ -11,7 +11,9 @@ Inputs (all under /root/reference/data/trajs, read-only):
     pins of Filter.propagate/update (FilterTraj / ImuRefTraj rows written by
     Filter.save, dvi_ekf/filter/Filter.py:457-465);
   * the legacy imu_ref_mandala0_mono_upd_Kp*_Km1.000.txt files, which pin the
-    interframe>1 interpolation / IMU-reference pose path.
+    interframe>1 interpolation / IMU-reference pose path;
+  * notch90.csv, the notch trajectory config.yaml names (an INPUT of the
+    with_notch flow; the reference holds no output for it).
 Output: tests/golden/reference_golden.npz (float64 arrays, compressed).
 """
 import os
@@ -32,6 +34,8 @@ def main():
         out[f"traj_{name}"] = np.loadtxt(os.path.join(REF, f"{name}.txt"))
     out["kf_best_mandala0_mono"] = np.loadtxt(os.path.join(REF, "kf_best_mandala0_mono.txt"))
     out["imu_ref_mandala0_mono"] = np.loadtxt(os.path.join(REF, "imu_ref_mandala0_mono.txt"))
+    # notch trajectory of config.yaml (notch_traj_name: notch90): "notch,notch_d,notch_dd" per camera frame, comma separated
+    out["notch_notch90"] = np.loadtxt(os.path.join(REF, "notch90.csv"), delimiter=",")
     for kp in ["0.006", "0.01", "2.0", "1.0"]:
         a = np.loadtxt(os.path.join(REF, f"imu_ref_mandala0_mono_upd_Kp{kp}_Km1.000.txt"))
         out[f"imu_ref_legacy_Kp{kp}"] = a

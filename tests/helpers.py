@@ -18,6 +18,7 @@ from oracle.eskf_oracle import (
     State,
     build_streams,
     camera_from_arrays,
+    camera_gen_rotated,
     quat_normalise,
 )
 
@@ -61,12 +62,14 @@ def model_kwargs(cfg: OracleConfig):
 class Scenario:
     """Everything needed to run one trajectory through the oracle and the engine."""
 
-    def __init__(self, traj, cfg: OracleConfig):
+    def __init__(self, traj, cfg: OracleConfig, notch=None):
         self.cfg = cfg
         self.probe = Probe(cfg.length, cfg.angle)
-        self.cam = camera_from_arrays(traj[:, 0], traj[:, 1:4], traj[:, 4:8], cfg)
+        self.cam = camera_from_arrays(traj[:, 0], traj[:, 1:4], traj[:, 4:8], cfg, notch=notch)
+        # with_notch: true -- the rotated camera is the IMU source / initial state / error reference (Camera.py:172-208)
+        self.rotated = camera_gen_rotated(self.cam, cfg) if notch is not None else None
         (self.x0s, self.u0, self.dt, self.om_acc, self.n_prop, self.cam_meas, self.notch_meas,
-         self.imu_ref_rows) = build_streams(self.cam, cfg, self.probe)
+         self.imu_ref_rows) = build_streams(self.cam, cfg, self.probe, self.rotated)
         self.x0 = self.x0s.as_vector()
         self.P0 = cfg.cov0_matrix
         kf = self.new_oracle()
@@ -81,9 +84,10 @@ class Scenario:
         return OracleFilter(self.cfg, x, self.P0 if P0 is None else P0, u[:3], u[3:], self.probe)
 
 
-def mandala_scenario(golden, n_frames=10, ifv=1, **cfg_kw):
+def mandala_scenario(golden, n_frames=10, ifv=1, with_notch=False, **cfg_kw):
     cfg = OracleConfig(max_vals=n_frames, interframe_vals=ifv, **cfg_kw)
-    return Scenario(golden["traj_mandala0_mono"][:n_frames], cfg)
+    notch = golden["notch_notch90"][:n_frames] if with_notch else None
+    return Scenario(golden["traj_mandala0_mono"][:n_frames], cfg, notch=notch)
 
 
 def random_filter_inputs(rng, n, cfg: OracleConfig, frozen=False):
