@@ -51,6 +51,9 @@
 
 namespace eskf {
 
+// Filter.calculate_update_mse is evaluated by the STAGER role at this step of the NEXT epoch (see role3_stage)
+constexpr int STATS_IT3 = 2;
+
 constexpr int RS3 = 26;          // row stride of the transposition buffer: even (16-byte rows) and
 constexpr int TB3_STRIDE = 632;  // 24*26 + 8; = 8 (mod 16) doubles => conflict-free STS.64 / LDS.128
 
@@ -244,7 +247,6 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
   double* sx = c.smem + L::SX + lane;
   d2* fxb = reinterpret_cast<d2*>(c.smem + L::FXB) + lane;  // pair j2 of slot s at fxb[(s * FX3_NPAIR + j2) * F]
   double p[3], v[3], q[4], Rwb[9], Rold[9];
-  double mse_last = 0.0, mse_sum = 0.0;
   if (act) {
     const double* xg = a.x + (c.f0 + lane) * NX;
     const double* rg = a.Ro + (c.f0 + lane) * 9;
@@ -331,17 +333,12 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
 #pragma unroll
         for (int i = 0; i < 3; ++i) sx[(SX3_V + 3 * s + i) * F] = v[i];
       }
-      if (a.cam_ref && a.imu_ref) {  // IMU half of Filter.calculate_update_mse (Filter.py:408-413)
-        const double* ir = a.imu_ref + (c.traj * a.E + e) * 6;
-        double ei[3], acc2 = 0.0;
-        euler_xyz_deg(q, ei);
+      if (a.cam_ref && a.imu_ref) {  // statistics of this update are evaluated later, off the critical path
+        double* xs = a.x + (c.f0 + lane) * NX;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const double d2_ = v[i] - ir[i], d3 = ei[i] - ir[3 + i];
-          acc2 += d2_ * d2_ + d3 * d3;
-        }
-        mse_last = acc2;
-        mse_sum += acc2;
+        for (int i = 0; i < 3; ++i) xs[3 + i] = v[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xs[6 + i] = q[i];
       }
     }
     scalar_barrier();  // U2 of the scalar roles done (the covariance warps do not wait: see role3_cov)
@@ -363,8 +360,6 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
     for (int i = 0; i < 6; ++i) ug[i] = uo[i * F];
 #pragma unroll
     for (int i = 0; i < 9; ++i) rg[i] = Rold[i];
-    sx[(SX3_ST + 0) * F] = mse_last;
-    sx[(SX3_ST + 1) * F] = mse_sum;
   }
   __syncthreads();  // tiles dumped, statistics partials written
   store_tiles3<F, NTHR>(a, c, threadIdx.x);
@@ -381,7 +376,7 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
   d2* fxb = reinterpret_cast<d2*>(c.smem + L::FXB) + lane;  // pair j2 of slot s at fxb[(s * FX3_NPAIR + j2) * F]
   const TRView<F> trv{sx + SX3_TR * F};
   double pc[3], qc[4], sig_om[3] = {0, 0, 0};
-  double mse_last = 0.0, mse_sum = 0.0, n_upd = 0.0;
+  double n_upd = 0.0;
   int32_t st = 0;
   if (act) {
     const double* xg = a.x + (c.f0 + lane) * NX;
@@ -492,17 +487,12 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
       } else {
         st |= ESKF_STATUS_UPDATE_SKIPPED;
       }
-      if (a.cam_ref && a.imu_ref) {  // camera half of Filter.calculate_update_mse (Filter.py:401-406)
-        const double* cr = a.cam_ref + (c.traj * a.E + e) * 6;
-        double ec[3], acc2 = 0.0;
-        euler_xyz_deg(qc, ec);
+      if (a.cam_ref && a.imu_ref) {  // statistics of this update are evaluated later, off the critical path
+        double* xs = a.x + (c.f0 + lane) * NX;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const double d0 = cr[i] - pc[i], d1 = cr[3 + i] - ec[i];
-          acc2 += d0 * d0 + d1 * d1;
-        }
-        mse_last = acc2;
-        mse_sum += acc2;
+        for (int i = 0; i < 3; ++i) xs[19 + i] = pc[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xs[22 + i] = qc[i];
       }
     }
     scalar_barrier();  // U2 of the scalar roles done (the covariance warps do not wait: see role3_cov)
@@ -514,8 +504,6 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
 #pragma unroll
     for (int i = 0; i < 4; ++i) xg[22 + i] = qc[i];
     a.status[c.f0 + lane] = st;
-    sx[(SX3_ST + 2) * F] = mse_last;
-    sx[(SX3_ST + 3) * F] = mse_sum;
     sx[(SX3_ST + 4) * F] = n_upd;
     sx[(SX3_ST + 5) * F] = (double)st;
   }
@@ -697,6 +685,42 @@ __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int l
     for (int i = 0; i < 7; ++i) sx[(SX3_MEAS + i) * F] = cam[i];
     sx[(SX3_MEAS + 7) * F] = notch;
   };
+  // Filter.calculate_update_mse (Filter.py:397-418) for both halves.  The Euler angles cost two atan2 and an asin per
+  // half (~3,500 dependent cycles); evaluated by the IMU / CAMERA roles at the update they delayed the first Jacobian
+  // record of the next epoch, for which every covariance warp is waiting (0.32 ms of 5.9 per launch).  Instead those
+  // roles park (v, q) / (p_cam, q_cam) in the filter's own row of the state array -- its final destination: the launch
+  // read the row in the prologue and rewrites it in the epilogue; ordered by the scalar barrier after U2 -- and this role,
+  // which has slack, evaluates the error terms at step STATS_IT3 of the next epoch (or before the next update, whichever
+  // comes first).  Same values, same summation order.  (The copies of the LAST update equal the final state the epilogue
+  // stores, so the last evaluation may overlap that store.)
+  double mseA_last = 0.0, mseA_sum = 0.0, mseB_last = 0.0, mseB_sum = 0.0;
+  bool pend = false;
+  auto flush_stats = [&](int64_t se) {
+    if (!pend) return;
+    pend = false;
+    const double* xs = a.x + (c.f0 + lane) * NX;
+    const double* ir = a.imu_ref + (c.traj * a.E + se) * 6;
+    const double* cr = a.cam_ref + (c.traj * a.E + se) * 6;
+    double xr[26];
+#pragma unroll
+    for (int i = 3; i < 10; ++i) xr[i] = __ldcg(xs + i);
+#pragma unroll
+    for (int i = 19; i < 26; ++i) xr[i] = __ldcg(xs + i);
+    double ei[3], ec[3], accA = 0.0, accB = 0.0;
+    euler_xyz_deg(xr + 6, ei);
+    euler_xyz_deg(xr + 22, ec);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double d2_ = xr[3 + i] - ir[i], d3 = ei[i] - ir[3 + i];
+      accA += d2_ * d2_ + d3 * d3;
+      const double d0 = cr[i] - xr[19 + i], d1 = cr[3 + i] - ec[i];
+      accB += d0 * d0 + d1 * d1;
+    }
+    mseA_last = accA;
+    mseA_sum += accA;
+    mseB_last = accB;
+    mseB_sum += accB;
+  };
   if (act) {
     const double* ug = a.u + (c.f0 + lane) * 6;
 #pragma unroll
@@ -709,7 +733,10 @@ __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int l
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
     if (act && a.do_update) stage_meas(e);
-    for (int it = 0; it < n; ++it) {
+    const int fl = n < STATS_IT3 ? n : STATS_IT3;
+    for (int it = 0;; ++it) {
+      if (it == fl && act) flush_stats(e - 1);
+      if (it >= n) break;
       if (act && k + it + 1 < a.T && ESKF3_SCALAR_ON(it)) stage_sample(k + it + 1);
       scalar_barrier();
     }
@@ -719,6 +746,14 @@ __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int l
     __syncthreads();  // U0 | U1
     __syncthreads();  // U1 | U2
     scalar_barrier();  // U2 of the scalar roles done (the covariance warps do not wait: see role3_cov)
+    pend = a.cam_ref && a.imu_ref;
+  }
+  if (act) {
+    flush_stats(a.E - 1);
+    sx[(SX3_ST + 0) * F] = mseA_last;
+    sx[(SX3_ST + 1) * F] = mseA_sum;
+    sx[(SX3_ST + 2) * F] = mseB_last;
+    sx[(SX3_ST + 3) * F] = mseB_sum;
   }
   __syncthreads();
   store_tiles3<F, NTHR>(a, c, threadIdx.x);

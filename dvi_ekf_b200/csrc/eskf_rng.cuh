@@ -72,10 +72,44 @@ ESKF_HD void normal4(uint64_t seed, uint64_t filter, uint64_t step, uint32_t kin
   box_muller32(c[2], c[3], z + 2);
 }
 
-// z[0..7]: eight normals of (filter, step, kind); the IMU stream uses z[0..5], the camera stream z[0..6]
+// two Philox blocks side by side as ONE rolled loop over the ten rounds (12 instructions in the body instead of
+// 2 x 60 unrolled ones: the generator runs in the STAGER role, off the critical path, and the step loop of
+// eskf_kernel3 is short of instruction cache, not of integer issue slots)
+ESKF_HD void philox4x32_10_x2(uint32_t* a, uint32_t* b, uint32_t k0, uint32_t k1) {
+#ifdef ESKF_RNG_ROLLED
+#pragma unroll 1
+#else
+#pragma unroll
+#endif
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t pa0 = (uint64_t)0xD2511F53u * a[0], pa1 = (uint64_t)0xCD9E8D57u * a[2];
+    const uint64_t pb0 = (uint64_t)0xD2511F53u * b[0], pb1 = (uint64_t)0xCD9E8D57u * b[2];
+    const uint32_t a0 = (uint32_t)(pa1 >> 32) ^ a[1] ^ k0, a2 = (uint32_t)(pa0 >> 32) ^ a[3] ^ k1;
+    const uint32_t b0 = (uint32_t)(pb1 >> 32) ^ b[1] ^ k0, b2 = (uint32_t)(pb0 >> 32) ^ b[3] ^ k1;
+    a[0] = a0;
+    a[1] = (uint32_t)pa1;
+    a[2] = a2;
+    a[3] = (uint32_t)pa0;
+    b[0] = b0;
+    b[1] = (uint32_t)pb1;
+    b[2] = b2;
+    b[3] = (uint32_t)pb0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+// z[0..7]: eight normals of (filter, step, kind) = normal4 of draw 0 and draw 1; the IMU stream uses z[0..5], the camera
+// stream z[0..6]
 ESKF_HD void normal8(uint64_t seed, uint64_t filter, uint64_t step, uint32_t kind, double* z) {
-  normal4(seed, filter, step, kind, 0, z);
-  normal4(seed, filter, step, kind, 1, z + 4);
+  const uint32_t hi = (uint32_t)(step >> 32) << 8;
+  uint32_t a[4] = {(uint32_t)step, kind * 16u + 0u + hi, (uint32_t)filter, (uint32_t)(filter >> 32)};
+  uint32_t b[4] = {(uint32_t)step, kind * 16u + 1u + hi, (uint32_t)filter, (uint32_t)(filter >> 32)};
+  philox4x32_10_x2(a, b, (uint32_t)seed, (uint32_t)(seed >> 32));
+  box_muller32(a[0], a[1], z);
+  box_muller32(a[2], a[3], z + 2);
+  box_muller32(b[0], b[1], z + 4);
+  box_muller32(b[2], b[3], z + 6);
 }
 
 }  // namespace eskf

@@ -22,16 +22,18 @@ def main():
     ap.add_argument("--variants", default="1,2")
     ap.add_argument("--fpc", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--stats", action="store_true", help="also time the launch with the error statistics on (what bench.py times)")
     a = ap.parse_args()
     wl = Workload()
     s = wl.s
     dev = torch.device("cuda")
     t = lambda x, dt=torch.float64: torch.tensor(np.ascontiguousarray(x), dtype=dt, device=dev)
-    d = dict(dt=t(s.dt), oa=t(s.om_acc), npr=t(s.n_prop, torch.int32), cam=t(s.cam), notch=t(s.notch))
+    d = dict(dt=t(s.dt), oa=t(s.om_acc), npr=t(s.n_prop, torch.int32), cam=t(s.cam), notch=t(s.notch), cam_ref=t(s.cam_ref),
+             imu_ref=t(s.imu_ref))
     for N in [int(v) for v in a.n.split(",")]:
         x0, P0, u0 = t(mc_initial_states(s.x0, N, 0)), t(wl.P0[None]), t(s.u0[None])
         for var in [int(v) for v in a.variants.split(",")]:
-            for noise in (False, True):
+            for noise, stats in ((False, False), (True, False)) + (((True, True),) if a.stats else ()):
                 bf = BatchFilter(N, variant=var, **wl.model)
                 bf.set_tuning(a.fpc)
                 bf.set_noise(wl.Qd[None], wl.Rd[None], wl.sig_om[None])
@@ -43,11 +45,15 @@ def main():
                     e1 = torch.cuda.Event(enable_timing=True)
                     kw = dict(imu_noise_std=wl.imu_std, cam_noise_std=wl.cam_std, seed=SEED) if noise else {}
                     e0.record()
-                    bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], want_stats=False, **kw)
+                    if stats:
+                        bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], cam_ref=d["cam_ref"], imu_ref=d["imu_ref"],
+                               stats_on_device=True, **kw)
+                    else:
+                        bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], want_stats=False, **kw)
                     e1.record()
                     torch.cuda.synchronize()
                     best = min(best, e0.elapsed_time(e1))
-                print(f"variant={var} N={N} noise={noise}: {best:.3f} ms -> {N * len(s.dt) / best * 1e3:.3e} filter-steps/s",
+                print(f"variant={var} N={N} noise={noise} stats={stats}: {best:.3f} ms -> {N * len(s.dt) / best * 1e3:.3e} filter-steps/s",
                       flush=True)
                 bf.close()
 
