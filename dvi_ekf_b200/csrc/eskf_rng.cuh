@@ -72,15 +72,11 @@ ESKF_HD void normal4(uint64_t seed, uint64_t filter, uint64_t step, uint32_t kin
   box_muller32(c[2], c[3], z + 2);
 }
 
-// two Philox blocks side by side as ONE rolled loop over the ten rounds (12 instructions in the body instead of
-// 2 x 60 unrolled ones: the generator runs in the STAGER role, off the critical path, and the step loop of
-// eskf_kernel3 is short of instruction cache, not of integer issue slots)
+// two Philox blocks side by side (the two draws of normal8: independent chains for the integer pipe).  Kept unrolled:
+// a rolled loop over the ten rounds is 100 instructions shorter but lengthens the STAGER role's step and cost 2.5 % of the
+// whole kernel (profiles/r01_s4_experiments.md)
 ESKF_HD void philox4x32_10_x2(uint32_t* a, uint32_t* b, uint32_t k0, uint32_t k1) {
-#ifdef ESKF_RNG_ROLLED
-#pragma unroll 1
-#else
 #pragma unroll
-#endif
   for (int r = 0; r < 10; ++r) {
     const uint64_t pa0 = (uint64_t)0xD2511F53u * a[0], pa1 = (uint64_t)0xCD9E8D57u * a[2];
     const uint64_t pb0 = (uint64_t)0xD2511F53u * b[0], pb1 = (uint64_t)0xCD9E8D57u * b[2];
