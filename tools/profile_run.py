@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--passes", type=int, default=3)
     ap.add_argument("--fpc", type=int, default=0)
     ap.add_argument("--frames", type=int, default=0, help="truncate the trajectory to this many camera epochs (0 = all)")
+    ap.add_argument("--no-noise", action="store_true", help="noise-free run (the Monte-Carlo generator is not executed)")
+    ap.add_argument("--no-stats", action="store_true", help="no error statistics")
     a = ap.parse_args()
     wl = Workload()
     s = wl.s
@@ -40,8 +42,12 @@ def main():
         bf.set_state(d["x0"], d["P0"], d["u0"], None)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], cam_ref=d["cam_ref"], imu_ref=d["imu_ref"],
-               stats_on_device=True, seed=SEED, imu_noise_std=wl.imu_std, cam_noise_std=wl.cam_std)
+        kw = {} if a.no_noise else dict(seed=SEED, imu_noise_std=wl.imu_std, cam_noise_std=wl.cam_std)
+        if a.no_stats:
+            bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], want_stats=False, **kw)
+        else:
+            bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], cam_ref=d["cam_ref"], imu_ref=d["imu_ref"],
+                   stats_on_device=True, **kw)
         e1.record()
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
