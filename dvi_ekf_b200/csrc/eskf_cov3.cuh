@@ -119,20 +119,22 @@ ESKF_HD void fx3_load_transposed(double (&X)[24][3], const double* rows) {
 
 // Pass 1: T(:, tile) = Fx X, row i stored as out[i * OS + v] as soon as it is finished (X is not modified;
 // the next pass starts from the transposed tile).
-// Rows 9:15 of Fx are identity rows (the DOF errors are random walks), so T(9:15, :) = P(9:15, :), whose transpose
-// the lanes 3 and 4 already hold: it is their own, unmodified tile.  With STORE_DOF_ROWS = false those six rows
-// are not stored and lanes 3 and 4 must skip the transposed reload (fx3_reload_skips_lane).
-ESKF_HD bool fx3_reload_skips_lane(int g) { return g == 3 || g == 4; }
-template <int PS, int OS, bool STORE_DOF_ROWS = true>
+// ALL 24 rows are exchanged, the identity rows 9:15 of Fx included.  (T(9:15, :) = P(9:15, :), and a symmetric P would
+// let lanes 3 and 4 keep their own tile instead of reloading it -- an earlier version did, and saved 18 stores per lane.
+// But the stored matrix is only symmetric up to rounding: with that shortcut the tiles of lanes 3 and 4 follow
+// G' = Fx G Fx^T while all others follow G' = Fx G^T Fx^T, which turns the antisymmetric rounding noise of the
+// dof / other cross blocks into a symmetric perturbation at every step.  With the default tuning nothing shows; with
+// process noise 10x smaller -- a fifth of the BASELINE config-3 grid -- the asymmetry grew tenfold per epoch and the
+// filter blew up after 15 updates where the oracle and the first kernel stay together at 1e-10:
+// tests/test_hostcheck.py::test_free_running_low_process_noise, tests/test_gpu_full_size.py.)
+template <int PS, int OS>
 ESKF_HD void fx3_apply_store(const double (&X)[24][3], const d2* f2, double* out) {
   const double dt = f2[(FX3_DT / 2) * PS].x;
   // identity rows of Fx: dofs 9:15 and notch'' 17
-  if (STORE_DOF_ROWS) {
 #pragma unroll
-    for (int i = 9; i < 15; ++i)
+  for (int i = 9; i < 15; ++i)
 #pragma unroll
-      for (int v = 0; v < 3; ++v) out[i * OS + v] = X[i][v];
-  }
+    for (int v = 0; v < 3; ++v) out[i * OS + v] = X[i][v];
 #pragma unroll
   for (int v = 0; v < 3; ++v) out[17 * OS + v] = X[17][v];
   double y[3][3], z[3][3];

@@ -17,7 +17,7 @@
 //   warps 4.. COVARIANCE  eight lanes per filter, lane g keeps columns 3g..3g+2 of the 24x24 covariance in
 //                   REGISTERS (72 doubles) for the whole launch -- see eskf_cov3.cuh for the algebra:
 //                   one propagation = two local sparse products around ONE transposition through shared
-//                   memory (72 STS.64 + 36 LDS.128 per lane); the camera update (gain, Joseph form,
+//                   memory (72 STS.64 + 36 LDS.128 per lane: all 24 rows, see eskf_cov3.cuh); the camera update (gain, Joseph form,
 //                   reset) works on the same register tile and exchanges only S, K, K R, W(:,h) (7-wide
 //                   records) between the eight lanes of a filter, with warp-level synchronisation.
 // Inside an epoch (the IMU steps between two camera frames) the scalar roles and the covariance warps are
@@ -898,9 +898,9 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
       if (ESKF3_COV_ON) {
         const d2* f2 = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
         // pass 1: T(:, 3g..3g+2) = Fx P(:, 3g..3g+2), rows stored as they are finished
-        fx3_apply_store<F, RS3, false>(X, f2, Tb + 3 * cg);
+        fx3_apply_store<F, RS3>(X, f2, Tb + 3 * cg);
         __syncwarp(gmask);
-        if (!fx3_reload_skips_lane(cg)) load_rows();  // X[k][v] = T(3g+v, k); lanes 3, 4: their own tile is that already
+        load_rows();  // X[k][v] = T(3g+v, k) -- every lane, the identity rows 9:15 included (eskf_cov3.cuh)
         // the record of the NEXT step is waited for here, behind the latency of the transposed reload, so that
         // nothing stands between the end of this step and the first coefficient fetch of the next one
         if (it + 1 < n) fx_slot_wait(c.mbar, kk + 1);

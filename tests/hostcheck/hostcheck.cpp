@@ -105,12 +105,11 @@ void hc_propagate3(const double* model, double* x, double* P, double* u, double*
   double T[24][24];
   for (int g = 0; g < 8; ++g) {
     for (int i = 0; i < 24; ++i) for (int v = 0; v < 3; ++v) X[g][i][v] = P[i * 24 + 3 * g + v];
-    fx3_apply_store<1, 24, false>(X[g], f2, &T[0][0] + 3 * g);  // the identity rows 9:15 are not exchanged ...
+    fx3_apply_store<1, 24>(X[g], f2, &T[0][0] + 3 * g);  // all 24 rows are exchanged (eskf_cov3.cuh)
   }
   auto qdf = [&](int j) { return qd[j]; };
   for (int g = 0; g < 8; ++g) {
-    if (!fx3_reload_skips_lane(g))  // ... lanes 3 and 4 keep their own tile instead (symmetry of P)
-      for (int k = 0; k < 24; ++k) for (int v = 0; v < 3; ++v) X[g][k][v] = T[3 * g + v][k];
+    for (int k = 0; k < 24; ++k) for (int v = 0; v < 3; ++v) X[g][k][v] = T[3 * g + v][k];
     fx3_apply_inplace<1>(X[g], f2);
     double qdv[3];
     fx3_noise_diag(g, qdf, qdv);

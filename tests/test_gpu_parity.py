@@ -243,3 +243,29 @@ def test_imu_noise_in_Q_matches_oracle(BatchFilter, golden):
     xg, Pg, *_ = bf.get_state()
     xr, Pr, *_ = kf.get_vectors()
     assert state_err(xg[1], xr) < TOL and cov_err(Pg[1], Pr) < TOL
+
+
+@pytest.mark.parametrize("variant", [3, 1])
+def test_free_running_low_process_noise(BatchFilter, golden, variant):
+    """Regression (see tests/test_hostcheck.py::test_free_running_low_process_noise): DOF random walks 10x smaller than
+    config.yaml, 40 epochs in one launch.  The stored covariance must stay symmetric to rounding and with the oracle."""
+    sc = mandala_scenario(golden, n_frames=41, ifv=10)
+    Qd = sc.Qd.copy()
+    Qd[6:12] *= 0.01
+    kf = sc.new_oracle()
+    kf.Q = np.diag(Qd)
+    k = 0
+    for e in range(len(sc.n_prop)):
+        for _ in range(sc.n_prop[e]):
+            kf.propagate(sc.dt[k], sc.om_acc[k, :3], sc.om_acc[k, 3:])
+            k += 1
+        assert kf.update(sc.cam_meas[e, :3], sc.cam_meas[e, 3:], sc.notch_meas[e]) is not None
+    xr, Pr, _, _ = kf.get_vectors()
+    with BatchFilter(5, variant=variant, **model_kwargs(sc.cfg)) as bf:
+        bf.set_noise(Qd[None], sc.Rd[None], sc.sig_om[None])
+        bf.set_state(sc.x0[None], sc.P0[None], sc.u0[None], None)
+        bf.run(sc.dt, sc.om_acc, sc.n_prop, sc.cam_meas, sc.notch_meas, want_stats=False)
+        xg, Pg, _, _, st = bf.get_state()
+    assert np.all(st == 0)
+    asym = np.abs(Pg[0] - Pg[0].T).max() / np.abs(Pg[0]).max()
+    assert state_err(xg[0], xr) < 1e-7 and cov_err(Pg[0], Pr, sc.Rd) < 1e-7 and asym < 1e-11, (state_err(xg[0], xr), cov_err(Pg[0], Pr, sc.Rd), asym)
