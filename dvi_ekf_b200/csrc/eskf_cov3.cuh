@@ -295,6 +295,15 @@ ESKF_HD void u3_get4(const double* rec, int j, double (&o)[4]) {
 
 // owner of measurement row m: column h_m = ESKF_HSET(m) belongs to lane h_m / 3, tile column h_m % 3
 // U0a: lanes 5..7 publish their columns of S (Filter.py:355); every lane files H P for its own columns.
+//
+// ORIENTATION.  The reference's covariance is symmetric only up to ITS rounding, and after an ill-conditioned update that
+// is not small: 2.6e-11 relative at a point of the BASELINE tuning grid, where reading the other triangle moves the next
+// update by 3e-8.  The tile is the transpose of the reference's matrix, X[k][v] = P(3g+v, k), whenever an update runs
+// (eskf_kernel3.cuh keeps it that way: every propagation flips the orientation, and an odd number of them is followed by
+// one explicit transposition).  With that orientation rows h of the tile are the reference's P H^T (the operand of the
+// gain), W = (I - K H) X and X' = W (I - K H)^T + K R K^T are the transposes of the reference's products, and the one
+// thing that must be turned around is S: the tile entry X[h_i][h_m] is P(h_m, h_i) = S(m, i), filed at (m, i).
+// (tests/test_hostcheck.py::test_lockstep_ill_conditioned_tuning: 1e-14 with, 3e-8 without.)
 template <int QS>
 ESKF_HD void upd3_publish_S(const double (&X)[24][3], int g, const double* rd, double* rec) {
 #pragma unroll
@@ -302,7 +311,7 @@ ESKF_HD void upd3_publish_S(const double (&X)[24][3], int g, const double* rd, d
     const int h = ESKF_HSET(m);
     if (g == h / 3) {
 #pragma unroll
-      for (int i = 0; i < 7; ++i) u3_at<QS>(rec, U3_S + 7 * i + m) = X[ESKF_HSET(i)][h % 3] + ((i == m) ? rd[m] : 0.0);
+      for (int i = 0; i < 7; ++i) u3_at<QS>(rec, U3_S + 7 * m + i) = X[ESKF_HSET(i)][h % 3] + ((i == m) ? rd[m] : 0.0);
     }
 #pragma unroll
     for (int v = 0; v < 3; ++v) u3_at<QS>(rec, U3_HP + 24 * m + 3 * g + v) = X[h][v];

@@ -886,6 +886,25 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
     }
   };
 
+  // Orientation of the tile (eskf_cov3.cuh, upd3_publish_S): X is the TRANSPOSE of the reference's matrix after the load
+  // (rows used as columns) and every propagation flips it (X' = Fx X^T Fx^T).  The update and the final store want the
+  // transposed orientation, so an odd number of propagations is followed by one explicit transposition through the
+  // buffer (the same exchange as inside a step, without the products; never needed with an even number of IMU samples
+  // per frame).  The covariance is symmetric only up to the reference's own rounding, which an ill-conditioned tuning
+  // makes large enough to matter.
+  bool flipped = false;
+  auto restore_orientation = [&]() {
+    if (!flipped) return;
+    flipped = false;
+#pragma unroll
+    for (int i = 0; i < 24; ++i)
+#pragma unroll
+      for (int v = 0; v < 3; ++v) Tb[i * RS3 + 3 * cg + v] = X[i][v];
+    __syncwarp(gmask);
+    load_rows();
+    __syncwarp(gmask);
+  };
+
   load_rows();
   __syncthreads();  // prologue
 
@@ -918,7 +937,9 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
       fx_slot_release(c.mbar, kk);  // this warp is done with the record
     }
     k += n;
+    if (ESKF3_COV_ON && (n & 1)) flipped = !flipped;
     if (!a.do_update) continue;
+    restore_orientation();
     // ---- U0: S and its inverse (the scalar CAMERA role computes the residual meanwhile) ----
 #ifdef ESKF_EXP_NO_UPDATE  // (profiling experiment: propagation only)
     __syncthreads();
@@ -960,6 +981,7 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
     // no CTA barrier here: the scalar roles go on to the first steps of the next epoch while the covariance warps
     // finish the Joseph form (what they exchange next is ordered by the record pipeline and by the next U0 | U1)
   }
+  restore_orientation();
   dump_rows();
   __syncthreads();
   store_tiles3<F, NTHR>(a, c, threadIdx.x);

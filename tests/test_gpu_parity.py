@@ -269,3 +269,63 @@ def test_free_running_low_process_noise(BatchFilter, golden, variant):
     assert np.all(st == 0)
     asym = np.abs(Pg[0] - Pg[0].T).max() / np.abs(Pg[0]).max()
     assert state_err(xg[0], xr) < 1e-7 and cov_err(Pg[0], Pr, sc.Rd) < 1e-7 and asym < 1e-11, (state_err(xg[0], xr), cov_err(Pg[0], Pr, sc.Rd), asym)
+
+
+@pytest.mark.parametrize("variant", [3, 1])
+def test_free_running_unfrozen_dofs(BatchFilter, golden, variant):
+    """The calibration use case: all six DOFs estimated (config.yaml freezes them), perturbed initial DOFs, 40 epochs in one
+    launch, several filters with different initial DOFs in one batch."""
+    sc = mandala_scenario(golden, n_frames=41, ifv=10, frozen_dofs=[False] * 6)
+    rng = np.random.default_rng(5)
+    n = 6
+    x0 = np.repeat(sc.x0[None], n, 0)
+    x0[:, 10:13] += rng.normal(0, np.deg2rad(3.0), (n, 3))
+    x0[:, 13:16] += rng.normal(0, 3.0, (n, 3))
+    with BatchFilter(n, variant=variant, **model_kwargs(sc.cfg)) as bf:
+        bf.set_noise(sc.Qd[None], sc.Rd[None], sc.sig_om[None])
+        bf.set_state(x0, sc.P0[None], sc.u0[None], None)
+        bf.run(sc.dt, sc.om_acc, sc.n_prop, sc.cam_meas, sc.notch_meas, want_stats=False)
+        xg, Pg, _, _, st = bf.get_state()
+    assert np.all(st == 0)
+    for i in (0, 3, n - 1):
+        kf = sc.new_oracle(x0=x0[i])
+        k = 0
+        for e in range(len(sc.n_prop)):
+            for _ in range(sc.n_prop[e]):
+                kf.propagate(sc.dt[k], sc.om_acc[k, :3], sc.om_acc[k, 3:])
+                k += 1
+            assert kf.update(sc.cam_meas[e, :3], sc.cam_meas[e, 3:], sc.notch_meas[e]) is not None
+        xr, Pr, _, _ = kf.get_vectors()
+        assert np.abs(xr[10:16] - x0[i, 10:16]).max() > 0.1  # the DOFs really move
+        assert state_err(xg[i], xr) < 1e-8 and cov_err(Pg[i], Pr, sc.Rd) < 1e-8, (i, state_err(xg[i], xr), cov_err(Pg[i], Pr, sc.Rd))
+
+
+@pytest.mark.parametrize("variant,n_frames,ifv", [(3, 31, 10), (1, 31, 10), (3, 12, 33)])
+def test_free_running_ill_conditioned_tuning(BatchFilter, golden, variant, n_frames, ifv):
+    """A point of the BASELINE config-3 grid where the REFERENCE's covariance is asymmetric at ~3e-11 and the orientation in
+    which it is consumed matters at 3e-8 per update (tests/test_hostcheck.py::test_lockstep_ill_conditioned_tuning).  30
+    epochs in one launch; 33 samples per frame makes the number of propagations per epoch odd (explicit re-orientation of
+    the register tile before every update, eskf_kernel3.cuh).  The oracle itself answers a one-ulp perturbation of its
+    inputs with 4e-9 after 30 epochs here."""
+    sc = mandala_scenario(golden, n_frames=n_frames, ifv=ifv)
+    Qd, Rd = sc.Qd.copy(), sc.Rd.copy()
+    Qd[6:9] *= 0.018478497974222907 ** 2
+    Qd[9:12] *= 0.11659144011798317 ** 2
+    Rd[0:3] *= 398.1071705534977 ** 2
+    Rd[3:6] *= 3.981071705534973 ** 2
+    kf = sc.new_oracle()
+    kf.Q, kf.R = np.diag(Qd), np.diag(Rd)
+    k = 0
+    for e in range(len(sc.n_prop)):
+        for _ in range(sc.n_prop[e]):
+            kf.propagate(sc.dt[k], sc.om_acc[k, :3], sc.om_acc[k, 3:])
+            k += 1
+        assert kf.update(sc.cam_meas[e, :3], sc.cam_meas[e, 3:], sc.notch_meas[e]) is not None
+    xr, Pr, _, _ = kf.get_vectors()
+    with BatchFilter(3, variant=variant, **model_kwargs(sc.cfg)) as bf:
+        bf.set_noise(Qd[None], Rd[None], sc.sig_om[None])
+        bf.set_state(sc.x0[None], sc.P0[None], sc.u0[None], None)
+        bf.run(sc.dt, sc.om_acc, sc.n_prop, sc.cam_meas, sc.notch_meas, want_stats=False)
+        xg, Pg, _, _, st = bf.get_state()
+    assert np.all(st == 0)
+    assert state_err(xg[0], xr) < 1e-7 and cov_err(Pg[0], Pr, Rd) < 1e-7, (state_err(xg[0], xr), cov_err(Pg[0], Pr, Rd))
