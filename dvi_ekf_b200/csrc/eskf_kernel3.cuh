@@ -888,23 +888,10 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
 
   // Orientation of the tile (eskf_cov3.cuh, upd3_publish_S): X is the TRANSPOSE of the reference's matrix after the load
   // (rows used as columns) and every propagation flips it (X' = Fx X^T Fx^T).  The update and the final store want the
-  // transposed orientation, so an odd number of propagations is followed by one explicit transposition through the
-  // buffer (the same exchange as inside a step, without the products; never needed with an even number of IMU samples
-  // per frame).  The covariance is symmetric only up to the reference's own rounding, which an ill-conditioned tuning
-  // makes large enough to matter.
-  bool flipped = false;
-  auto restore_orientation = [&]() {
-    if (!flipped) return;
-    flipped = false;
-#pragma unroll
-    for (int i = 0; i < 24; ++i)
-#pragma unroll
-      for (int v = 0; v < 3; ++v) Tb[i * RS3 + 3 * cg + v] = X[i][v];
-    __syncwarp(gmask);
-    load_rows();
-    __syncwarp(gmask);
-  };
-
+  // transposed orientation, so an epoch with an odd number of propagations gets one more pass through the exchange of
+  // the step loop -- plain stores instead of pass 1, no pass 2 -- which turns the tile back (never with an even number
+  // of IMU samples per frame).  The covariance is symmetric only up to the reference's own rounding, which an
+  // ill-conditioned tuning makes large enough to matter.
   load_rows();
   __syncthreads();  // prologue
 
@@ -912,18 +899,28 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
     if (n > 0) fx_slot_wait(c.mbar, k);  // the Jacobian record of the first step of the epoch is complete
-    for (int it = 0; it < n; ++it) {
+    const int n_ex = ESKF3_COV_ON ? n + (n & 1) : n;  // (one exchange more after an odd number of propagations)
+    for (int it = 0; it < n_ex; ++it) {
       const int64_t kk = k + it;
+      const bool step = it < n;
       if (ESKF3_COV_ON) {
         const d2* f2 = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
-        // pass 1: T(:, 3g..3g+2) = Fx P(:, 3g..3g+2), rows stored as they are finished
-        fx3_apply_store<F, RS3>(X, f2, Tb + 3 * cg);
+        if (step) {
+          // pass 1: T(:, 3g..3g+2) = Fx P(:, 3g..3g+2), rows stored as they are finished
+          fx3_apply_store<F, RS3>(X, f2, Tb + 3 * cg);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 24; ++i)
+#pragma unroll
+            for (int v = 0; v < 3; ++v) Tb[i * RS3 + 3 * cg + v] = X[i][v];
+        }
         __syncwarp(gmask);
         load_rows();  // X[k][v] = T(3g+v, k) -- every lane, the identity rows 9:15 included (eskf_cov3.cuh)
         // the record of the NEXT step is waited for here, behind the latency of the transposed reload, so that
         // nothing stands between the end of this step and the first coefficient fetch of the next one
         if (it + 1 < n) fx_slot_wait(c.mbar, kk + 1);
         __syncwarp(gmask);
+        if (!step) break;
         // pass 2: P'(3g+v, :) = Fx T(3g+v, :)^T
         fx3_apply_inplace<F>(X, f2);
         // (the lane index is laundered through an empty asm so that the thirteen selected addends of the diagonal
@@ -937,9 +934,7 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
       fx_slot_release(c.mbar, kk);  // this warp is done with the record
     }
     k += n;
-    if (ESKF3_COV_ON && (n & 1)) flipped = !flipped;
     if (!a.do_update) continue;
-    restore_orientation();
     // ---- U0: S and its inverse (the scalar CAMERA role computes the residual meanwhile) ----
 #ifdef ESKF_EXP_NO_UPDATE  // (profiling experiment: propagation only)
     __syncthreads();
@@ -981,7 +976,6 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
     // no CTA barrier here: the scalar roles go on to the first steps of the next epoch while the covariance warps
     // finish the Joseph form (what they exchange next is ordered by the record pipeline and by the next U0 | U1)
   }
-  restore_orientation();
   dump_rows();
   __syncthreads();
   store_tiles3<F, NTHR>(a, c, threadIdx.x);

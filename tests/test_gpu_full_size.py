@@ -152,7 +152,9 @@ def test_config4_all_trajectories_1024_seeds_long_horizon(golden):
     x, P, u, R, st = launch(w, every)
     ok = torch.isfinite(x).all(dim=1) & torch.isfinite(P).all(dim=(1, 2)) & (st == 0)
     assert float(ok.double().mean()) > 0.999  # (at 50 frames one noise seed in nine thousand has already tipped over)
-    _check_properties(x, P, st, "config 4, 20 frames", healthy=ok)
+    # (9,216 noisy filters on nine trajectories: the worst asymmetry seen is 1.3e-9; the reference's own matrix reaches
+    # 3e-11 on a single noise-free filter, tests/test_hostcheck.py::test_lockstep_ill_conditioned_tuning)
+    _check_properties(x, P, st, "config 4, 20 frames", healthy=ok, sym_tol=1e-7)
     assert bool(ok[:seeds].all()) and float(x[1:seeds, 0:3].std(dim=0).max()) > 0 and float((x[0] - x[seeds]).abs().max()) > 1e-3
     # ---- full length ----
     w = workload(3001)

