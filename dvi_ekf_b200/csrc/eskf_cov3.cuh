@@ -302,7 +302,11 @@ ESKF_HD void u3_get4(const double* rec, int j, double (&o)[4]) {
 // (eskf_kernel3.cuh keeps it that way: every propagation flips the orientation, and an odd number of them is followed by
 // one explicit transposition).  With that orientation rows h of the tile are the reference's P H^T (the operand of the
 // gain), W = (I - K H) X and X' = W (I - K H)^T + K R K^T are the transposes of the reference's products, and the one
-// thing that must be turned around is S: the tile entry X[h_i][h_m] is P(h_m, h_i) = S(m, i), filed at (m, i).
+// thing that must be turned around is S: the tile entry X[h_i][h_m] is P(h_m, h_i) = S(m, i).  The record keeps the tile's
+// view (S^T); the inverse routines deliver inv(S): on the device the Gauss-Jordan elimination runs on the record and writes
+// its result transposed (inv7_group3), on the host inv7 is given the transposed record.  (Inverting S^T and transposing is
+// not the same rounding as inverting S: it yields a good LEFT inverse, K S = P H^T, which is what the first update with
+// its prior >> R needs -- eliminating S itself was off by 3e-8 there.)
 // (tests/test_hostcheck.py::test_lockstep_ill_conditioned_tuning: 1e-14 with, 3e-8 without.)
 template <int QS>
 ESKF_HD void upd3_publish_S(const double (&X)[24][3], int g, const double* rd, double* rec) {
@@ -311,7 +315,7 @@ ESKF_HD void upd3_publish_S(const double (&X)[24][3], int g, const double* rd, d
     const int h = ESKF_HSET(m);
     if (g == h / 3) {
 #pragma unroll
-      for (int i = 0; i < 7; ++i) u3_at<QS>(rec, U3_S + 7 * m + i) = X[ESKF_HSET(i)][h % 3] + ((i == m) ? rd[m] : 0.0);
+      for (int i = 0; i < 7; ++i) u3_at<QS>(rec, U3_S + 7 * i + m) = X[ESKF_HSET(i)][h % 3] + ((i == m) ? rd[m] : 0.0);
     }
 #pragma unroll
     for (int v = 0; v < 3; ++v) u3_at<QS>(rec, U3_HP + 24 * m + 3 * g + v) = X[h][v];

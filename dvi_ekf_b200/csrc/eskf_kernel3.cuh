@@ -838,7 +838,8 @@ __device__ __forceinline__ bool inv7_group3(double* rec, int g) {
   ok = ok && (chk == 0.0);
   if (g < 7) {
 #pragma unroll
-    for (int j = 0; j < 7; ++j) u3_at<QS>(rec, U3_SINV + 7 * myk + (int)((plist >> (3 * j)) & 7u)) = a[j];
+    // (written TRANSPOSED: the record holds the tile's view of S, the transpose of the reference's -- eskf_cov3.cuh)
+    for (int j = 0; j < 7; ++j) u3_at<QS>(rec, U3_SINV + 7 * (int)((plist >> (3 * j)) & 7u) + myk) = a[j];
   }
   const unsigned bal = __ballot_sync(FULL, ok);
   const unsigned lane = threadIdx.x & 31u;

@@ -133,7 +133,7 @@ int hc_update3(const double* model, double* x, double* P, const double* u, const
   alignas(16) double rec[U3_SIZE];
   for (int g = 0; g < 8; ++g) upd3_publish_S<1>(X[g], g, rd, rec);
   double S[49], Si[49];
-  for (int j = 0; j < 49; ++j) S[j] = rec[U3_S + j];
+  for (int i = 0; i < 7; ++i) for (int j = 0; j < 7; ++j) S[7 * i + j] = rec[U3_S + 7 * j + i];  // the record holds S^T (eskf_cov3.cuh)
   bool ok = inv7(S, Si);
   for (int j = 0; j < 49; ++j) rec[U3_SINV + j] = Si[j];
   double res[7];
