@@ -24,6 +24,11 @@ import time
 
 import numpy as np
 
+# stdout carries ONE JSON line: NCCL prints its "NCCL version ..." banner to stdout at the levels VERSION (set on the GPU
+# boxes) and WARN; the level is switched off before anything loads NCCL (an explicit INFO / TRACE of the user is left alone)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    os.environ["NCCL_DEBUG"] = "NONE"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
