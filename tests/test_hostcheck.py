@@ -195,3 +195,45 @@ def test_lockstep_ill_conditioned_tuning(hc, golden, fn, ufn):
             assert state_err(x, xr) < TOL and cov_err(P, Pr, Rd) < 1e-6
     assert asym > 1e-12  # the reference's own covariance is not symmetric here
     assert ws < 1e-11 and wP < 1e-11, (ws, wP)
+
+
+@pytest.mark.parametrize("fn,ufn", [("hc_propagate", "hc_update"), ("hc_propagate3", "hc_update3")])
+def test_lockstep_random_tunings(hc, golden, fn, ufn):
+    """Sixteen random points of the BASELINE config-3 tuning space (DOF random walks x 1e-2 .. 1e2, camera measurement noise
+    x 1e-3 .. 1e3), six epochs each in lock step.  The first update of every run (prior >> R, with these scales up to 1e21)
+    is excluded from the covariance check: the reference does not determine it (tests/test_conditioning.py; both device
+    paths differ from the oracle by the same 0.2 there)."""
+    sc = mandala_scenario(golden, n_frames=7, ifv=10)
+    model = _model(sc.cfg)
+    rng = np.random.default_rng(11)
+    wps = wpP = wus = wuP = 0.0
+    for _ in range(16):
+        a, b = 10 ** rng.uniform(-2, 2, 2)
+        c, d = 10 ** rng.uniform(-3, 3, 2)
+        Qd, Rd = sc.Qd.copy(), sc.Rd.copy()
+        Qd[6:9] *= b ** 2
+        Qd[9:12] *= a ** 2
+        Rd[0:3] *= c ** 2
+        Rd[3:6] *= d ** 2
+        kf = sc.new_oracle()
+        kf.Q, kf.R = np.diag(Qd), np.diag(Rd)
+        k = 0
+        for e in range(len(sc.n_prop)):
+            for _ in range(sc.n_prop[e]):
+                x, P, u, Ro = [v.copy() for v in kf.get_vectors()]
+                kf.propagate(sc.dt[k], sc.om_acc[k, :3], sc.om_acc[k, 3:])
+                oa = sc.om_acc[k].copy()
+                getattr(hc, fn)(_p(model), _p(x), _p(P), _p(u), _p(Ro), sc.dt[k], _p(oa), _p(Qd), _p(sc.sig_om), None)
+                xr, Pr, _, _ = kf.get_vectors()
+                wps, wpP = max(wps, state_err(x, xr)), max(wpP, cov_err(P, Pr))
+                k += 1
+            x, P, u, Ro = [v.copy() for v in kf.get_vectors()]
+            assert kf.update(sc.cam_meas[e, :3], sc.cam_meas[e, 3:], sc.notch_meas[e]) is not None
+            cm = sc.cam_meas[e].copy()
+            Kd = np.zeros((24, 7))
+            assert getattr(hc, ufn)(_p(model), _p(x), _p(P), _p(u), _p(Ro), _p(cm), sc.notch_meas[e], _p(Rd), _p(Kd)) == 1
+            xr, Pr, _, _ = kf.get_vectors()
+            if e > 0:
+                wus, wuP = max(wus, state_err(x, xr)), max(wuP, cov_err(P, Pr, Rd))
+    assert wps < TOL and wpP < TOL, (wps, wpP)
+    assert wus < 1e-11 and wuP < 1e-11, (wus, wuP)
