@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -78,12 +79,209 @@ __global__ void noise_dump_kernel(double* out, uint64_t seed, int64_t filter_id0
   for (int j = 0; j < 8; ++j) out[i * 8 + j] = z[j];
 }
 
+// ---- pre- / post-pass of eskf_run (KArgs::imu_pf / meas_pf / snap) -------------------------------------------------
+// The Monte-Carlo generator and the Euler angles of Filter.calculate_update_mse are throughput work with no dependence on
+// the filters' recursion.  Inside the persistent kernel they ran on ONE warp of every CTA and slowed the whole CTA through
+// that warp's sub-partition (12 % of the launch at 4096 filters, profiles/r02_*); as separate, fully parallel kernels they
+// cost a few per cent of that.  Same generator, same operations in the same order: the results are bit-identical
+// (tests/test_gpu_noise.py compares both paths).
+struct PPArgs {
+  int64_t N, T, E;
+  int n_traj;
+  int64_t fpt, filter_id0;
+  uint64_t seed;
+  double imu_noise[6], cam_noise[7];
+  int noise_on, noise_free0, noise_mod, per_filter;
+};
+
+__device__ __forceinline__ void pp_ids(const PPArgs& p, int64_t f, int64_t& traj, int64_t& gid, bool& noisy) {
+  const int64_t g = p.filter_id0 + f;
+  traj = (p.n_traj > 1) ? g / p.fpt : 0;
+  gid = p.noise_mod > 0 ? g % p.noise_mod : g;
+  noisy = p.noise_on && !(p.noise_free0 && gid == 0);
+}
+
+// out[(j N + f) 6 + i]: IMU sample of step j as filter f sees it (role3_stage::stage_sample)
+__global__ void pp_imu_kernel(double* __restrict__ out, const double* __restrict__ om_acc, const PPArgs p) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.T * p.N) return;
+  const int64_t j = idx / p.N, f = idx - j * p.N;
+  int64_t traj, gid;
+  bool noisy;
+  pp_ids(p, f, traj, gid, noisy);
+  const double* src = p.per_filter ? om_acc + (f * p.T + j) * 6 : om_acc + (traj * p.T + j) * 6;
+  double u[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) u[i] = src[i];
+  if (noisy) {
+    double z[8];
+    normal8(p.seed, (uint64_t)gid, (uint64_t)j, RNG_KIND_IMU, z);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) u[i] += p.imu_noise[i] * z[i];
+  }
+  double* dst = out + idx * 6;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) dst[i] = u[i];
+}
+
+// out[(e N + f) 8 + i]: camera measurement of epoch e as filter f sees it: position, raw quaternion, notch angle
+// (role3_stage::stage_meas)
+__global__ void pp_meas_kernel(double* __restrict__ out, const double* __restrict__ camm, const double* __restrict__ notchm,
+                               const PPArgs p) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.E * p.N) return;
+  const int64_t e = idx / p.N, f = idx - e * p.N;
+  int64_t traj, gid;
+  bool noisy;
+  pp_ids(p, f, traj, gid, noisy);
+  const int64_t mrow = traj * p.E + e;
+  double cam[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) cam[i] = camm[mrow * 7 + i];
+  double notch = notchm[mrow];
+  if (noisy) {
+    double z[8];
+    normal8(p.seed, (uint64_t)gid, (uint64_t)e, RNG_KIND_CAM, z);
+    double dth[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      cam[i] += p.cam_noise[i] * z[i];
+      dth[i] = p.cam_noise[3 + i] * z[3 + i];
+    }
+    double dq[4], qn[4];
+    quat_about_axis(sqrt(dth[0] * dth[0] + dth[1] * dth[1] + dth[2] * dth[2]), dth, dq);
+    const double nq = sqrt(cam[3] * cam[3] + cam[4] * cam[4] + cam[5] * cam[5] + cam[6] * cam[6]);
+    quat_mul(cam + 3, dq, qn);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cam[3 + i] = qn[i] * nq;
+    notch += p.cam_noise[6] * z[6];
+  }
+  double* dst = out + idx * 8;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) dst[i] = cam[i];
+  dst[7] = notch;
+}
+
+// Filter.calculate_update_mse (Filter.py:397-418) from the per-epoch snapshots snap[(e N + f) 14]: v q p_cam q_cam after
+// every update.  Stage 1, one thread per (epoch, filter): the two squared-error sums of the epoch (the same operations as
+// role3_stage's flush_stats), written over the first two entries of the snapshot.  Stage 2, one thread per filter: the
+// running sums over the epochs IN ORDER (the same additions as in the kernel), rows [7] (last epoch) and [8] (sum over
+// the epochs) of the statistics, and their contribution to stats_sum.
+__global__ void pp_stats1_kernel(double* __restrict__ snap, const double* __restrict__ cam_ref,
+                                 const double* __restrict__ imu_ref, const PPArgs p) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.E * p.N) return;
+  const int64_t e = idx / p.N, f = idx - e * p.N;
+  int64_t traj, gid;
+  bool noisy;
+  pp_ids(p, f, traj, gid, noisy);
+  double* xs = snap + idx * 14;
+  const double* ir = imu_ref + (traj * p.E + e) * 6;
+  const double* cr = cam_ref + (traj * p.E + e) * 6;
+  double xr[14];
+#pragma unroll
+  for (int i = 0; i < 14; ++i) xr[i] = xs[i];
+  double ei[3], ec[3], accA = 0.0, accB = 0.0;
+  euler_xyz_deg(xr + 3, ei);
+  euler_xyz_deg(xr + 10, ec);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double d2_ = xr[i] - ir[i], d3 = ei[i] - ir[3 + i];
+    accA += d2_ * d2_ + d3 * d3;
+    const double d0 = cr[i] - xr[7 + i], d1 = cr[3 + i] - ec[i];
+    accB += d0 * d0 + d1 * d1;
+  }
+  xs[0] = accA;
+  xs[1] = accB;
+}
+
+__global__ void pp_stats2_kernel(const double* __restrict__ snap, double* stats_out, double* stats_sum, const PPArgs p) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double r7 = 0.0, r8 = 0.0;
+  if (f < p.N) {
+    double mseA_last = 0.0, mseA_sum = 0.0, mseB_last = 0.0, mseB_sum = 0.0;
+    for (int64_t e = 0; e < p.E; ++e) {
+      const double* xs = snap + (e * p.N + f) * 14;
+      mseA_last = xs[0];
+      mseA_sum += mseA_last;
+      mseB_last = xs[1];
+      mseB_sum += mseB_last;
+    }
+    r7 = (mseA_last + mseB_last) / 12.0;
+    r8 = (mseA_sum + mseB_sum) / 12.0;
+    if (stats_out) {
+      stats_out[f * ESKF_NSTAT + 7] = r7;
+      stats_out[f * ESKF_NSTAT + 8] = r8;
+    }
+  }
+  if (stats_sum) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      r7 += __shfl_xor_sync(0xffffffffu, r7, o);
+      r8 += __shfl_xor_sync(0xffffffffu, r8, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(stats_sum + 7, r7);
+      atomicAdd(stats_sum + 8, r8);
+    }
+  }
+}
+
+// ---- reduction of the statistics rows (the vector a multi-GPU launcher all-reduces) -----------------------------------
+// stats_sum of eskf_run, from the per-filter rows, DETERMINISTICALLY (fixed summation tree, no atomics: the same bits
+// whatever the CTA scheduling) and MASKED: a filter that diverged (non-finite row) or whose status word is set would
+// otherwise turn the reduced vector of a million healthy filters into NaN.  [0:10] sums over the healthy filters,
+// [10] filters with a non-zero status, [11] healthy filters (the divisor of every mean), [12] non-finite filters.
+constexpr int RED_ROWS = 4096;  // rows per block
+__global__ void stats_partial_kernel(const double* __restrict__ rows, const int32_t* __restrict__ status, int64_t n,
+                                     double* __restrict__ partial) {
+  __shared__ double sh[256][13];
+  const int64_t r0 = (int64_t)blockIdx.x * RED_ROWS;
+  double acc[13];
+#pragma unroll
+  for (int i = 0; i < 13; ++i) acc[i] = 0.0;
+  for (int64_t r = r0 + threadIdx.x; r < r0 + RED_ROWS && r < n; r += 256) {
+    const double* row = rows + r * ESKF_NSTAT;
+    double v[10], chk = 0.0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      v[i] = row[i];
+      chk += v[i] * 0.0;  // NaN / inf detector
+    }
+    const bool fin = (chk == 0.0), flagged = status[r] != 0;
+    if (fin && !flagged) {
+#pragma unroll
+      for (int i = 0; i < 10; ++i) acc[i] += v[i];
+      acc[11] += 1.0;
+    }
+    if (flagged) acc[10] += 1.0;
+    if (!fin) acc[12] += 1.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 13; ++i) sh[threadIdx.x][i] = acc[i];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+#pragma unroll
+      for (int i = 0; i < 13; ++i) sh[threadIdx.x][i] += sh[threadIdx.x + o][i];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < ESKF_NSTAT) partial[(int64_t)blockIdx.x * ESKF_NSTAT + threadIdx.x] = threadIdx.x < 13 ? sh[0][threadIdx.x] : 0.0;
+}
+__global__ void stats_final_kernel(const double* __restrict__ partial, int64_t nblk, double* __restrict__ out) {
+  if (threadIdx.x >= ESKF_NSTAT) return;
+  double a = 0.0;
+  for (int64_t b = 0; b < nblk; ++b) a += partial[b * ESKF_NSTAT + threadIdx.x];
+  out[threadIdx.x] = a;
+}
+
 thread_local std::string g_err;
 
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-constexpr int N_STAGE = 9;
+constexpr int N_STAGE = 13;  // 0..8: arguments / results of the calls; 9..11: pre- / post-pass buffers of eskf_run; 12: partial sums
 struct eskf_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -92,8 +290,8 @@ struct eskf_handle {
   double *x = nullptr, *P = nullptr, *u = nullptr, *Ro = nullptr, *par = nullptr;
   int32_t* status = nullptr;
   // grow-only device staging for host-side arguments / results
-  void* stage[N_STAGE] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t stage_sz[N_STAGE] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  void* stage[N_STAGE] = {};
+  size_t stage_sz[N_STAGE] = {};
   double* stats_sum_dev = nullptr;
   int64_t launches = 0;
   int fpc = 0;  // filters per CTA (0 = automatic)
@@ -133,6 +331,16 @@ static int stage_in(eskf_t* h, int slot, const void* src, size_t bytes, int mem,
   CK(cudaMemcpyAsync(h->stage[slot], src, bytes, cudaMemcpyHostToDevice, h->stream));
   *out = h->stage[slot];
   return ESKF_OK;
+}
+
+// memory the pre- / post-pass buffers of one eskf_run may take (ESKF_B200_PP_MAX_BYTES; 0 switches the mode off and the
+// generator / the statistics run inside the persistent kernel as in round 1)
+static size_t pp_budget_bytes() {
+  static const size_t v = [] {
+    const char* e = getenv("ESKF_B200_PP_MAX_BYTES");
+    return e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)32 << 30);
+  }();
+  return v;
 }
 
 static const int kShapes1[] = {28, 24, 20, 16, 12, 8, 4};  // eskf_kernel  (v1)
@@ -217,6 +425,7 @@ static void base_args(const eskf_t* h, KArgs& a) {
 }
 
 extern "C" {
+static int create_alloc(eskf_t* h, const eskf_model_t* model, int64_t n_filters, int device, void* cuda_stream);
 
 const char* eskf_last_error(void) { return g_err.c_str(); }
 const char* eskf_version(void) { return "eskf_b200 0.3 (sm_100a)"; }
@@ -228,6 +437,18 @@ int eskf_create(const eskf_model_t* model, int64_t n_filters, int device, void* 
   }
   CK(cudaSetDevice(device));
   eskf_t* h = new eskf_handle();
+  const int rc_alloc = create_alloc(h, model, n_filters, device, cuda_stream);
+  if (rc_alloc != ESKF_OK) {
+    const std::string keep = g_err;  // (eskf_destroy does not touch it, but keep the first error whatever happens)
+    eskf_destroy(h);
+    g_err = keep;
+    return rc_alloc;
+  }
+  *out = h;
+  return ESKF_OK;
+}
+
+static int create_alloc(eskf_t* h, const eskf_model_t* model, int64_t n_filters, int device, void* cuda_stream) {
   h->device = device;
   h->stream = (cudaStream_t)cuda_stream;
   h->N = n_filters;
@@ -253,7 +474,6 @@ int eskf_create(const eskf_model_t* model, int64_t n_filters, int device, void* 
   CK(cudaMemsetAsync(h->Ro, 0, n * 9 * sizeof(double), h->stream));
   CK(cudaMemsetAsync(h->par, 0, n * PAR_STRIDE * sizeof(double), h->stream));
   CK(cudaMemsetAsync(h->status, 0, n * sizeof(int32_t), h->stream));
-  *out = h;
   return ESKF_OK;
 }
 
@@ -407,9 +627,38 @@ int eskf_run(eskf_t* h, const eskf_streams_t* sp, double* stats_out, double* sta
   const int smem_kind = sp->mem;
   const int64_t T = sp->n_steps, E = sp->n_epochs, nt = sp->n_traj;
   const int64_t fpt = nt > 1 ? sp->filters_per_traj : h->N;
-  if (nt > 1 && (fpt <= 0 || (sp->filter_id0 % fpt) != 0)) {
-    g_err = "eskf_run: filters_per_traj must divide filter_id0";
+  if (T < 0 || E < 0 || sp->filter_id0 < 0) {
+    g_err = "eskf_run: n_steps, n_epochs and filter_id0 must not be negative";
     return ESKF_EINVAL;
+  }
+  if (nt > 1) {
+    // the kernels pick the trajectory of a filter from its GLOBAL id: (filter_id0 + f) / filters_per_traj
+    if (fpt <= 0 || (sp->filter_id0 % fpt) != 0) {
+      g_err = "eskf_run: filter_id0 must be a multiple of filters_per_traj (a shard starts at a trajectory boundary)";
+      return ESKF_EINVAL;
+    }
+    if (sp->filter_id0 + h->N > nt * fpt) {
+      g_err = "eskf_run: filter_id0 + n_filters exceeds n_traj * filters_per_traj (the streams of " +
+              std::to_string((long long)nt) + " trajectories do not cover these filters)";
+      return ESKF_EINVAL;
+    }
+  }
+  if (smem_kind == ESKF_MEM_HOST) {  // (device-resident streams: the kernels clamp every epoch to what is left, epoch_steps3)
+    for (int64_t tr = 0; tr < nt; ++tr) {
+      int64_t tot = 0;
+      for (int64_t e = 0; e < E; ++e) {
+        const int32_t np_ = sp->n_prop[tr * E + e];
+        if (np_ < 0) {
+          g_err = "eskf_run: negative n_prop entry";
+          return ESKF_EINVAL;
+        }
+        tot += np_;
+      }
+      if (tot > T) {
+        g_err = "eskf_run: sum(n_prop) = " + std::to_string((long long)tot) + " exceeds n_steps = " + std::to_string((long long)T);
+        return ESKF_EINVAL;
+      }
+    }
   }
   const void *ddt, *doa, *dnp, *dcam, *dno, *dcr, *dir;
   int rc;
@@ -420,10 +669,10 @@ int eskf_run(eskf_t* h, const eskf_streams_t* sp, double* stats_out, double* sta
   if ((rc = stage_in(h, 4, sp->notch, (size_t)nt * E * sizeof(double), smem_kind, &dno))) return rc;
   if ((rc = stage_in(h, 5, sp->cam_ref, (size_t)nt * E * 6 * sizeof(double), smem_kind, &dcr))) return rc;
   if ((rc = stage_in(h, 6, sp->imu_ref, (size_t)nt * E * 6 * sizeof(double), smem_kind, &dir))) return rc;
-  double* dstats = nullptr;
-  const size_t sb = (size_t)h->N * ESKF_NSTAT * sizeof(double);
-  if (stats_out) {
-    if (mem == ESKF_MEM_DEVICE) {
+  double* dstats = nullptr;  // the per-filter rows live on the device whenever any statistic is wanted: stats_sum is reduced
+  const size_t sb = (size_t)h->N * ESKF_NSTAT * sizeof(double);  // from them after the launch (stats_partial_kernel)
+  if (stats_out || stats_sum) {
+    if (stats_out && mem == ESKF_MEM_DEVICE) {
       dstats = stats_out;
     } else {
       if ((rc = stage_reserve(h, 7, sb))) return rc;
@@ -441,10 +690,7 @@ int eskf_run(eskf_t* h, const eskf_streams_t* sp, double* stats_out, double* sta
     }
   }
   double* dsum = nullptr;
-  if (stats_sum) {
-    dsum = (mem == ESKF_MEM_DEVICE) ? stats_sum : h->stats_sum_dev;
-    CK(cudaMemsetAsync(dsum, 0, ESKF_NSTAT * sizeof(double), h->stream));
-  }
+  if (stats_sum) dsum = (mem == ESKF_MEM_DEVICE) ? stats_sum : h->stats_sum_dev;
   KArgs a;
   base_args(h, a);
   a.T = T;
@@ -462,7 +708,7 @@ int eskf_run(eskf_t* h, const eskf_streams_t* sp, double* stats_out, double* sta
   for (int i = 0; i < 6; ++i) a.gt_dofs[i] = sp->gt_dofs[i];
   a.do_update = 1;
   a.stats_out = dstats;
-  a.stats_sum = dsum;
+  a.stats_sum = nullptr;  // (the kernels' own atomic sums are not used any more: see stats_partial_kernel)
   a.trace = dtrace;
   a.seed = sp->seed;
   a.noise_free0 = sp->noise_free_filter0;
@@ -475,7 +721,65 @@ int eskf_run(eskf_t* h, const eskf_streams_t* sp, double* stats_out, double* sta
     a.cam_noise[i] = sp->cam_noise_std[i];
     if (a.cam_noise[i] != 0.0) a.noise_on = 1;
   }
+  // ---- pre- / post-pass mode (eskf_kernel3, F = 28 and the smaller shapes alike): see PPArgs above ----
+  bool pp_stats = false;
+  PPArgs pp;
+  memset(&pp, 0, sizeof(pp));
+#if ESKF_OPT_PP
+  if (kernel_of(h) == 3 && pp_budget_bytes() > 0 && T > 0 && E > 0) {
+    pp.N = h->N;
+    pp.T = T;
+    pp.E = E;
+    pp.n_traj = (int)nt;
+    pp.fpt = fpt;
+    pp.filter_id0 = sp->filter_id0;
+    pp.seed = sp->seed;
+    for (int i = 0; i < 6; ++i) pp.imu_noise[i] = a.imu_noise[i];
+    for (int i = 0; i < 7; ++i) pp.cam_noise[i] = a.cam_noise[i];
+    pp.noise_on = a.noise_on;
+    pp.noise_free0 = a.noise_free0;
+    pp.noise_mod = a.noise_mod;
+    pp.per_filter = 0;
+    const bool want_stats = dcr && dir && dstats;
+    const size_t b_imu = a.noise_on ? (size_t)h->N * T * 6 * sizeof(double) : 0;
+    const size_t b_meas = a.noise_on ? (size_t)h->N * E * 8 * sizeof(double) : 0;
+    const size_t b_snap = want_stats ? (size_t)h->N * E * 14 * sizeof(double) : 0;
+    if (b_imu + b_meas + b_snap <= pp_budget_bytes()) {
+      if (a.noise_on) {
+        if ((rc = stage_reserve(h, 9, b_imu))) return rc;
+        if ((rc = stage_reserve(h, 10, b_meas))) return rc;
+        const int64_t n1 = h->N * T, n2 = h->N * E;
+        pp_imu_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, h->stream>>>((double*)h->stage[9], a.om_acc, pp);
+        pp_meas_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, h->stream>>>((double*)h->stage[10], a.cam, a.notch, pp);
+        CK(cudaGetLastError());
+        h->launches += 2;
+        a.imu_pf = (const double*)h->stage[9];
+        a.meas_pf = (const double*)h->stage[10];
+      }
+      if (want_stats) {
+        if ((rc = stage_reserve(h, 11, b_snap))) return rc;
+        a.snap = (double*)h->stage[11];
+        pp_stats = true;
+      }
+    }
+  }
+#endif
   if ((rc = launch(h, a, fpt, nt > 1))) return rc;
+  if (pp_stats) {
+    const int64_t n2 = h->N * E;
+    pp_stats1_kernel<<<(unsigned)((n2 + 127) / 128), 128, 0, h->stream>>>(a.snap, a.cam_ref, a.imu_ref, pp);
+    pp_stats2_kernel<<<(unsigned)((h->N + 63) / 64), 64, 0, h->stream>>>(a.snap, dstats, nullptr, pp);
+    CK(cudaGetLastError());
+    h->launches += 2;
+  }
+  if (dsum) {
+    const int64_t nblk = (h->N + RED_ROWS - 1) / RED_ROWS;
+    if ((rc = stage_reserve(h, 12, (size_t)nblk * ESKF_NSTAT * sizeof(double)))) return rc;
+    stats_partial_kernel<<<(unsigned)nblk, 256, 0, h->stream>>>(dstats, h->status, h->N, (double*)h->stage[12]);
+    stats_final_kernel<<<1, 32, 0, h->stream>>>((const double*)h->stage[12], nblk, dsum);
+    CK(cudaGetLastError());
+    h->launches += 2;
+  }
   if (dtrace && smem_kind == ESKF_MEM_HOST) {
     CK(cudaMemcpyAsync(sp->trace_x, dtrace, tb, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -516,30 +820,35 @@ int eskf_fp64_peak(int device, void* cuda_stream, int repeats, double* tflops_ou
   int smc = 0;
   CK(cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, device));
   double* d = nullptr;
-  CK(cudaMalloc(&d, 64));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
   constexpr int ILP = 16;
   const int blocks = smc * 8, threads = 256, iters = 1 << 14;
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
-  dfma_peak_kernel<ILP><<<blocks, threads, 0, st>>>(d, iters, 1.0000001, 1e-9);  // warm-up
   double best = 1e30;
-  for (int r = 0; r < repeats; ++r) {
-    CK(cudaEventRecord(e0, st));
-    dfma_peak_kernel<ILP><<<blocks, threads, 0, st>>>(d, iters, 1.0000001, 1e-9);
-    CK(cudaEventRecord(e1, st));
-    CK(cudaEventSynchronize(e1));
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    if (ms < best) best = ms;
-  }
-  CK(cudaGetLastError());
+  auto body = [&]() -> int {  // (every resource is released below whichever call fails)
+    CK(cudaMalloc(&d, 64));
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    dfma_peak_kernel<ILP><<<blocks, threads, 0, st>>>(d, iters, 1.0000001, 1e-9);  // warm-up
+    for (int r = 0; r < repeats; ++r) {
+      CK(cudaEventRecord(e0, st));
+      dfma_peak_kernel<ILP><<<blocks, threads, 0, st>>>(d, iters, 1.0000001, 1e-9);
+      CK(cudaEventRecord(e1, st));
+      CK(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      if (ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    return ESKF_OK;
+  };
+  const int rc = body();
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (d) cudaFree(d);
+  if (rc) return rc;
   const double flops = 2.0 * ILP * (double)iters * blocks * threads;
   *tflops_out = flops / (best * 1e-3) * 1e-12;
   if (ms_out) *ms_out = best;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(d);
   return ESKF_OK;
 }
 
@@ -555,14 +864,18 @@ int eskf_noise_dump(int device, void* cuda_stream, uint64_t seed, int64_t filter
   const size_t bytes = (size_t)tot * 8 * sizeof(double);
   double* d = out;
   if (mem == ESKF_MEM_HOST) CK(cudaMalloc(&d, bytes));
-  noise_dump_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(d, seed, filter_id0, n_filters, step0, n_steps, (uint32_t)kind);
-  CK(cudaGetLastError());
-  if (mem == ESKF_MEM_HOST) {
-    CK(cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaFree(d));
-  }
-  return ESKF_OK;
+  auto body = [&]() -> int {
+    noise_dump_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(d, seed, filter_id0, n_filters, step0, n_steps, (uint32_t)kind);
+    CK(cudaGetLastError());
+    if (mem == ESKF_MEM_HOST) {
+      CK(cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    return ESKF_OK;
+  };
+  const int rc = body();
+  if (mem == ESKF_MEM_HOST) cudaFree(d);
+  return rc;
 }
 
 int64_t eskf_launch_count(const eskf_t* h) { return h ? h->launches : 0; }

@@ -17,6 +17,10 @@
 #pragma once
 #include "eskf_math.cuh"
 
+#ifndef ESKF_OPT_UPD
+#define ESKF_OPT_UPD 1  // hand-pipelined record fetches in the loops of the camera update
+#endif
+
 namespace eskf {
 
 // N consecutive coefficients starting at the (even) record offset base, held as pairs
@@ -200,6 +204,146 @@ ESKF_HD void fx3_apply_inplace(double (&X)[24][3], const d2* f2) {
   }
 }
 
+// Pass 2 fused with the transposed reload: X <- Fx T^T(:, tile), the operand T(3g+v, k) streamed from the rows 3g..3g+2 of
+// the transposition buffer (row stride RS doubles) pair by pair and consumed column by column, so that the 36 fetches of
+// the tile are spread over the 222 multiply-adds of the pass instead of preceding them as one burst (during which the FP64
+// pipe of the sub-partition idles: all covariance warps of a CTA run the same phase at the same time).  X is write-only
+// here.  Every accumulator sees the same operations in the same order as in fx3_apply_inplace after fx3_load_transposed:
+// the results are bit-identical (tests/test_hostcheck.py replays both).
+template <int PS, int RS>
+ESKF_HD void fx3_apply_stream(double (&X)[24][3], const d2* f2, const double* rows) {
+  const double dt = f2[(FX3_DT / 2) * PS].x;
+  auto ld = [&](int j, double (&lo)[3], double (&hi)[3]) {  // T(3g+v, 2j), T(3g+v, 2j+1)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      const d2 t = reinterpret_cast<const d2*>(rows + v * RS)[j];
+      lo[v] = t.x;
+      hi[v] = t.y;
+    }
+  };
+  // multiply-adds of one column k of a three-row group: y[i][v] += c(o + i) x[v]
+  auto col3 = [&](int r0, const Coefs<PS, 6>& c, int o, const double (&x)[3]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int v = 0; v < 3; ++v) X[r0 + i][v] += c(o + i) * x[v];
+  };
+  double o0[3], o1[3], o2[3], o3[3], o4[3], o5[3], o16[3], o17[3], o18[3], o19[3], o22[3], o23[3];
+  ld(1, o2, o3);
+  ld(2, o4, o5);
+  ld(8, o16, o17);
+  ld(9, o18, o19);
+  ld(11, o22, o23);
+  ld(0, o0, o1);
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    // rows 18:21 start from the mis-aligned identity block (quirk Q3) and dt v
+    X[18][v] = o16[v] + dt * o3[v];
+    X[19][v] = o17[v] + dt * o4[v];
+    X[20][v] = o18[v] + dt * o5[v];
+    // rows 21:24: Fx[22,22] = Fx[23,23] = 1
+    X[21][v] = 0.0;
+    X[22][v] = o22[v];
+    X[23][v] = o23[v];
+    // rows 0:3  p += dt v
+    X[0][v] = o0[v] + dt * o3[v];
+    X[1][v] = o1[v] + dt * o4[v];
+    X[2][v] = o2[v] + dt * o5[v];
+    // rows 3:6 start from v, rows 6:9 from zero
+    X[3][v] = o3[v];
+    X[4][v] = o4[v];
+    X[5][v] = o5[v];
+    X[6][v] = 0.0;
+    X[7][v] = 0.0;
+    X[8][v] = 0.0;
+    // notch chain, rows 16 and 17
+    X[16][v] = o16[v] + dt * o17[v];
+    X[17][v] = o17[v];
+  }
+  Coefs<PS, 6> h2a, h2b;
+  {  // columns 6, 7: C1 (rows 18:21), A and B (rows 3:9)
+    double x6[3], x7[3];
+    ld(3, x6, x7);
+    Coefs<PS, 6> h1, ab;
+    h1.load(f2, FX3_H1);
+    ab.load(f2, FX3_AB);
+    col3(18, h1, 0, x6);
+    col3(3, ab, 0, x6);
+    col3(6, ab, 3, x6);
+    ab.load(f2, FX3_AB + 6);
+    col3(18, h1, 3, x7);
+    col3(3, ab, 0, x7);
+    col3(6, ab, 3, x7);
+  }
+  {  // columns 8, 9: C1 / C2, A and B; D on dof 1 (rows 21:24)
+    double x8[3], x9[3];
+    ld(4, x8, x9);
+    Coefs<PS, 6> h1, ab;
+    h1.load(f2, FX3_H1 + 6);
+    ab.load(f2, FX3_AB + 12);
+    h2a.load(f2, FX3_H2);
+    col3(18, h1, 0, x8);
+    col3(3, ab, 0, x8);
+    col3(6, ab, 3, x8);
+    col3(18, h1, 3, x9);
+    col3(21, h2a, 0, x9);
+#pragma unroll
+    for (int v = 0; v < 3; ++v) X[9][v] = x9[v];
+  }
+  {  // columns 10, 11
+    double x10[3], x11[3];
+    ld(5, x10, x11);
+    Coefs<PS, 6> h1;
+    h1.load(f2, FX3_H1 + 12);
+    h2b.load(f2, FX3_H2 + 6);
+    col3(18, h1, 0, x10);
+    col3(21, h2a, 3, x10);
+    col3(18, h1, 3, x11);
+    col3(21, h2b, 0, x11);
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      X[10][v] = x10[v];
+      X[11][v] = x11[v];
+    }
+  }
+  {  // columns 12, 13
+    double x12[3], x13[3];
+    ld(6, x12, x13);
+    Coefs<PS, 6> h1;
+    h1.load(f2, FX3_H1 + 18);
+    col3(18, h1, 0, x12);
+    col3(18, h1, 3, x13);
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      X[12][v] = x12[v];
+      X[13][v] = x13[v];
+    }
+  }
+  {  // columns 14, 15: last column of C2; D on the notch angle; row 15 of the notch chain
+    double x14[3], x15[3];
+    ld(7, x14, x15);
+    Coefs<PS, 6> h1;
+    h1.load(f2, FX3_H1 + 24);
+    col3(18, h1, 0, x14);
+    col3(21, h2b, 3, x15);
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      X[14][v] = x14[v];
+      X[15][v] = x15[v] + dt * o16[v];
+    }
+  }
+  {  // columns 19, 20, 21: E (quirk Q3)
+    double x20[3], x21[3];
+    ld(10, x20, x21);
+    Coefs<PS, 6> h2c, h2d;
+    h2c.load(f2, FX3_H2 + 12);
+    h2d.load(f2, FX3_H2 + 18);
+    col3(21, h2c, 0, o19);
+    col3(21, h2c, 3, x20);
+    col3(21, h2d, 0, x21);
+  }
+}
+
 // this lane's share of the diagonal of Fi Q Fi^T: rows 3..14 get qd[r-3] (Fi[3:15,0:12] = I), row 17 gets
 // qd[12] (Fi[17,12] = 1); qdv[v] belongs to row 3g+v.  qd(j) = diag(Q)[j].
 template <typename QD>
@@ -313,10 +457,12 @@ ESKF_HD void upd3_publish_S(const double (&X)[24][3], int g, const double* rd, d
 #pragma unroll
   for (int m = 0; m < 7; ++m) {
     const int h = ESKF_HSET(m);
+#if !ESKF_OPT_UPD  // (with ESKF_OPT_UPD the inverse reads S from the H P record: S^T(i, m) = H P(i, h_m) + [i == m] R_m)
     if (g == h / 3) {
 #pragma unroll
       for (int i = 0; i < 7; ++i) u3_at<QS>(rec, U3_S + 7 * i + m) = X[ESKF_HSET(i)][h % 3] + ((i == m) ? rd[m] : 0.0);
     }
+#endif
 #pragma unroll
     for (int v = 0; v < 3; ++v) u3_at<QS>(rec, U3_HP + 24 * m + 3 * g + v) = X[h][v];
   }
@@ -366,6 +512,48 @@ ESKF_HD void upd3_gain(int g, double* rec, const double* res, double (&K)[3][7],
 template <int QS>
 ESKF_HD void upd3_w_pass(double (&X)[24][3], int g, double* rec) {
   // rows outside H (0..14, 16, 17): column by column of K, four rows at a time, X[i][v] -= K(i, m) P(h_m, j_v)
+#if ESKF_OPT_UPD
+  // Software pipelined by hand: the fetches of a block are issued two blocks ahead of the multiply-adds that use them, and
+  // those of the first blocks of column m + 1 at the end of column m.  (ptxas keeps the order of the fetches it is given: as
+  // written below -- fetch, use, fetch, use through ONE scratch quad -- every 16-byte fetch exposed its full latency, 12
+  // times per column: 667 cycles per column for 144 cycles of FP64 issue.)  Same operations in the same order per element.
+  {
+    double xh[3], ka[4], kb[4], kc[4];
+    auto pre = [&](int m) {
+#pragma unroll
+      for (int v = 0; v < 3; ++v) xh[v] = u3_get<QS>(rec, U3_HP + 24 * m + 3 * g + v);
+      u3_get4<QS>(rec, U3_K + 24 * m + 0, ka);
+      u3_get4<QS>(rec, U3_K + 24 * m + 4, kb);
+    };
+    auto blk = [&](int ib, const double (&k)[4], const double (&x)[3]) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int v = 0; v < 3; ++v) X[ib + r][v] -= k[r] * x[v];
+    };
+    pre(0);
+#pragma unroll 1
+    for (int m = 0; m < 7; ++m) {
+      const double x[3] = {xh[0], xh[1], xh[2]};
+      u3_get4<QS>(rec, U3_K + 24 * m + 8, kc);
+      blk(0, ka, x);
+      u3_get4<QS>(rec, U3_K + 24 * m + 12, ka);  // rows 12..15 (15 is an H row)
+      blk(4, kb, x);
+      u3_get4<QS>(rec, U3_K + 24 * m + 16, kb);  // rows 16, 17 (18, 19 are H rows)
+      blk(8, kc, x);
+      const double k12[3] = {ka[0], ka[1], ka[2]}, k16[2] = {kb[0], kb[1]};
+      pre(m < 6 ? m + 1 : 6);
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        X[12][v] -= k12[0] * x[v];
+        X[13][v] -= k12[1] * x[v];
+        X[14][v] -= k12[2] * x[v];
+        X[16][v] -= k16[0] * x[v];
+        X[17][v] -= k16[1] * x[v];
+      }
+    }
+  }
+#else
 #pragma unroll 1
   for (int m = 0; m < 7; ++m) {
     double xh[3];
@@ -392,6 +580,7 @@ ESKF_HD void upd3_w_pass(double (&X)[24][3], int g, double* rec) {
       X[17][v] -= k2[1] * xh[v];
     }
   }
+#endif
   // the seven rows h_a themselves (they still hold the prior)
   double w[7][3];
 #pragma unroll
@@ -429,7 +618,8 @@ ESKF_HD void upd3_w_pass(double (&X)[24][3], int g, double* rec) {
 //   W(:,j) (1 - K[j][a]) - sum_{m != a} W(:,h_m) K[j][m] + sum_m K(:,m) (R_m K[j][m])
 // then the reset P <- G P G^T with G = I - [delta_theta / 2]x on 6:9 and 21:24 (Filter.py:386-390).
 //   rd[m * RDS] = diag(R)[m]: read from memory inside the loop over m (a register array cannot be indexed by m)
-template <int QS, int RDS>
+//   dth[i * DS], dthc[i * DS]: the error-state rotations of the reset, read AFTER the loops (twelve registers less across them)
+template <int QS, int RDS, int DS>
 ESKF_HD void upd3_finish(double (&X)[24][3], int g, const double* rec, const double* rd, const double* dth,
                          const double* dthc) {
   // (1 - K[j][a]) for a column j = h_a measured directly, 1 otherwise: lanes 5 (column 15), 6 and 7
@@ -445,6 +635,53 @@ ESKF_HD void upd3_finish(double (&X)[24][3], int g, const double* rec, const dou
   for (int i = 0; i < 24; ++i)
 #pragma unroll
     for (int v = 0; v < 3; ++v) X[i][v] = cdv[v] * X[i][v];
+#if ESKF_OPT_UPD
+  {  // software pipelined by hand (see upd3_w_pass): fetches two blocks ahead, the next column's first blocks at the end
+    double kv[3], rdm, ba[4], bb[4], bc[4];
+    auto blk = [&](int ib, const double (&w)[4], const double (&z)[3], bool sub) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+          if (sub)
+            X[ib + r][v] -= w[r] * z[v];
+          else
+            X[ib + r][v] += w[r] * z[v];
+        }
+    };
+    // pass over m of ONE of the two sums: base = U3_WH (sub) or U3_K (add)
+    auto sweep = [&](int base, bool sub) {
+      auto pre = [&](int m) {
+#pragma unroll
+        for (int v = 0; v < 3; ++v) kv[v] = u3_get<QS>(rec, U3_K + 24 * m + 3 * g + v);
+        if (!sub) rdm = rd[m * RDS];
+        u3_get4<QS>(rec, base + 24 * m + 0, ba);
+        u3_get4<QS>(rec, base + 24 * m + 4, bb);
+      };
+      pre(0);
+#pragma unroll 1
+      for (int m = 0; m < 7; ++m) {
+        double z[3];
+#pragma unroll
+        for (int v = 0; v < 3; ++v) z[v] = sub ? ((u3_hset(m) == 3 * g + v) ? 0.0 : kv[v]) : rdm * kv[v];
+        u3_get4<QS>(rec, base + 24 * m + 8, bc);
+        blk(0, ba, z, sub);
+        u3_get4<QS>(rec, base + 24 * m + 12, ba);
+        blk(4, bb, z, sub);
+        u3_get4<QS>(rec, base + 24 * m + 16, bb);
+        blk(8, bc, z, sub);
+        u3_get4<QS>(rec, base + 24 * m + 20, bc);
+        blk(12, ba, z, sub);
+        const double b16[4] = {bb[0], bb[1], bb[2], bb[3]}, b20[4] = {bc[0], bc[1], bc[2], bc[3]};
+        pre(m < 6 ? m + 1 : 6);
+        blk(16, b16, z, sub);
+        blk(20, b20, z, sub);
+      }
+    };
+    sweep(U3_WH, true);
+    sweep(U3_K, false);
+  }
+#else
 #pragma unroll 1
   for (int m = 0; m < 7; ++m) {
     double kz[3];
@@ -478,8 +715,12 @@ ESKF_HD void upd3_finish(double (&X)[24][3], int g, const double* rec, const dou
         for (int v = 0; v < 3; ++v) X[ib + r][v] += k[r] * kjr[v];
     }
   }
-  const double gt[3] = {0.5 * dth[0], 0.5 * dth[1], 0.5 * dth[2]};
-  const double gc[3] = {0.5 * dthc[0], 0.5 * dthc[1], 0.5 * dthc[2]};
+#endif
+#if ESKF_OPT_UPD && defined(__CUDA_ARCH__)
+  asm volatile("" ::: "memory");  // the reset operands are fetched here, not before the loops
+#endif
+  const double gt[3] = {0.5 * dth[0], 0.5 * dth[DS], 0.5 * dth[2 * DS]};
+  const double gc[3] = {0.5 * dthc[0], 0.5 * dthc[DS], 0.5 * dthc[2 * DS]};
   // G P: rows 6:9 and 21:24 of every column;  (I - [g]x) = [[1, g2, -g1], [-g2, 1, g0], [g1, -g0, 1]]
 #pragma unroll
   for (int v = 0; v < 3; ++v) {

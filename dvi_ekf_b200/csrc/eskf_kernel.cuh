@@ -63,6 +63,12 @@ struct KArgs {
   int noise_on;
   int noise_free0;
   int noise_mod;  // > 0: noise id = global id % noise_mod
+  // pre- / post-pass mode of eskf_run (eskf_kernel3 only; see eskf_pp.cuh): per-filter streams prepared by a pre-pass
+  // kernel and per-epoch snapshots for the statistics post-pass, so that neither the Monte-Carlo generator nor the
+  // Euler angles of Filter.calculate_update_mse run inside the persistent kernel
+  const double* imu_pf;   // [T][N][6]  noisy IMU samples per filter, or nullptr
+  const double* meas_pf;  // [E][N][8]  noisy camera measurement (pos 3, quat 4, notch) per filter, or nullptr
+  double* snap;           // [E][N][14] v(3) q(4) p_cam(3) q_cam(4) after every update, or nullptr
 };
 
 // one FilterTraj row's worth of nominal state in the layout of x (include/eskf.h)

@@ -49,10 +49,61 @@
 #define ESKF3_COV_ON true
 #endif
 
+// optimisation switches of round 2 (each A/B-timed on the GPU, profiles/r02_*): 0 / 1
+#ifndef ESKF_OPT_LATEACQ
+#define ESKF_OPT_LATEACQ 0  // producers compute the step first and acquire the record slot only to store
+#endif
+#ifndef ESKF_OPT_SYNCW
+#define ESKF_OPT_SYNCW 1  // full-mask __syncwarp in the step loop of the covariance role
+#endif
+#ifndef ESKF_OPT_STATS_U0
+#define ESKF_OPT_STATS_U0 0  // Filter.calculate_update_mse evaluated during U0 / U1 of the next update instead of step 2
+#endif
+#ifndef ESKF_OPT_PP
+#define ESKF_OPT_PP 1  // per-filter streams from a pre-pass and statistics in a post-pass (KArgs::imu_pf / meas_pf / snap)
+#endif
+#ifndef ESKF_OPT_TMA
+#define ESKF_OPT_TMA 0  // sample stream staged by cp.async.bulk chunks (see CH3_STEPS)
+#endif
+#ifndef ESKF_OPT_STREAM
+#define ESKF_OPT_STREAM 1  // pass 2 streams the transposed tile from the buffer (reload fused into the pass)
+#endif
+
 namespace eskf {
+
+// ESKF_EXP_TIMING (profiling build): cycles per phase, accumulated by lane 0 of every warp into a global table
+// [CTA][warp][16], read back with eskf_debug_timing() (eskf_launch3.cu).  Not part of the product build.
+#if defined(ESKF_EXP_TIMING) && defined(ESKF_F)
+#define TIMING_SLOTS 16
+static __device__ long long g_eskf_timing[256 * 12 * TIMING_SLOTS];  // (one table per CTA-shape translation unit)
+struct PhaseTimer {  // (fire-and-forget global reductions: one register pair of state, no accumulators in registers)
+  long long t;
+  __device__ __forceinline__ PhaseTimer() { t = clock64(); }
+  __device__ __forceinline__ void mark(int slot) {
+    const long long n = clock64();
+    if ((threadIdx.x & 31) == 0 && blockIdx.x < 256)
+      atomicAdd(reinterpret_cast<unsigned long long*>(g_eskf_timing) + (blockIdx.x * 12 + (threadIdx.x >> 5)) * TIMING_SLOTS + slot,
+                (unsigned long long)(n - t));
+    t = n;
+  }
+  __device__ __forceinline__ void flush() {}
+};
+#define PT_DECL() PhaseTimer pt_
+#define PT_MARK(s) pt_.mark(s)
+#define PT_FLUSH() pt_.flush()
+#else
+#define PT_DECL()
+#define PT_MARK(s)
+#define PT_FLUSH()
+#endif
 
 // Filter.calculate_update_mse is evaluated by the STAGER role at this step of the NEXT epoch (see role3_stage)
 constexpr int STATS_IT3 = 2;
+
+// ESKF_OPT_TMA: the IMU sample stream (dt[T], om_acc[T,6]: shared by the filters of a trajectory) is staged through shared
+// memory in chunks of CH3_STEPS samples by bulk-asynchronous copies (cp.async.bulk, completion on an mbarrier), two chunks in
+// flight; the STAGER lanes then read the samples of a step from shared memory instead of seven broadcast global loads
+constexpr int CH3_STEPS = 16;
 
 constexpr int RS3 = 26;          // row stride of the transposition buffer: even (16-byte rows) and
 constexpr int TB3_STRIDE = 632;  // 24*26 + 8; = 8 (mod 16) doubles => conflict-free STS.64 / LDS.128
@@ -81,7 +132,14 @@ struct Lay3 {
   static constexpr int SX = F * TB3_STRIDE;     // [SX3_SIZE][F]
   static constexpr int FXB = SX + SX3_SIZE * F; // [2][FX3_NPAIR][F] d2
   static constexpr int MBAR = FXB + 2 * FX3_NPAIR * 2 * F;   // 4 mbarriers: full[2], empty[2]
+#if ESKF_OPT_TMA
+  static constexpr int CHBAR = MBAR + 4;                     // 2 mbarriers: chunk[2] of the staged sample stream
+  static constexpr int CHUNK = CHBAR + 2;                    // [2][CH3_STEPS * 7]: om_acc (6 per step) then dt (1 per step)
+  static constexpr int TOTAL = CHUNK + 2 * CH3_STEPS * 7;    // doubles
+  static_assert((CHUNK % 2) == 0, "16-byte alignment of the bulk-copy destination");
+#else
   static constexpr int TOTAL = MBAR + 4;                     // doubles
+#endif
   static_assert((SX % 2) == 0 && (FXB % 2) == 0, "16-byte alignment");
   static_assert(4 * U3_SIZE <= 4 * TB3_STRIDE, "update records must fit the transposition buffers of a warp");
 };
@@ -137,14 +195,29 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
     __nanosleep(64);
   }
 }
+// bulk-asynchronous copy global -> shared of `bytes` (multiple of 16, both addresses 16-byte aligned), completion counted
+// in bytes on the mbarrier (TMA unit: UBLKCP in SASS)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
 // step kk uses record slot kk & 1; its full barrier completes phase kk >> 1, and the slot is free for step kk
 // once the consumers of step kk - 2 have arrived on its empty barrier (phase (kk - 2) >> 1)
 __device__ __forceinline__ void fx_slot_acquire(uint64_t* mbar, int64_t kk) {  // producers, before writing
+#ifndef ESKF_EXP_NO_PIPE  // (profiling experiment: no coupling between the roles)
   if (kk >= 2) mbar_wait_relaxed(mbar + 2 + (kk & 1), (uint32_t)(((kk - 2) >> 1) & 1));
+#endif
 }
 __device__ __forceinline__ void fx_slot_publish(uint64_t* mbar, int64_t kk) { mbar_arrive_warp(mbar + (kk & 1)); }
 __device__ __forceinline__ void fx_slot_wait(uint64_t* mbar, int64_t kk) {  // consumers, before reading
+#ifndef ESKF_EXP_NO_PIPE
   mbar_wait(mbar + (kk & 1), (uint32_t)((kk >> 1) & 1));
+#endif
 }
 __device__ __forceinline__ void fx_slot_release(uint64_t* mbar, int64_t kk) { mbar_arrive_warp(mbar + 2 + (kk & 1)); }
 // barrier of the four scalar-role warps
@@ -152,6 +225,9 @@ __device__ __forceinline__ void scalar_barrier() { asm volatile("bar.sync 1, 128
 // JACOB -> CAMERA inside a step: the probe kinematics of the step are published (JACOB does not wait)
 __device__ __forceinline__ void pk_ready_arrive() { asm volatile("bar.arrive 2, 64;" ::: "memory"); }
 __device__ __forceinline__ void pk_ready_wait() { asm volatile("bar.sync 2, 64;" ::: "memory"); }
+
+struct Ctx3;
+__device__ __forceinline__ int epoch_steps3(const KArgs& a, const Ctx3& c, int64_t e, int64_t k);
 
 struct Ctx3 {
   double* smem;
@@ -163,6 +239,16 @@ struct Ctx3 {
   const double* dtp;
   uint64_t* mbar;  // full[2], empty[2]
 };
+
+// IMU steps of epoch e, k steps into the stream: n_prop[e] clamped to what is left of the stream, so that inconsistent
+// DEVICE-resident streams (sum(n_prop) > n_steps; host streams are validated by eskf_run) can never index past the sample
+// stream, the ring or the trace rows
+__device__ __forceinline__ int epoch_steps3(const KArgs& a, const Ctx3& c, int64_t e, int64_t k) {
+  if (!c.n_prop) return (int)a.T;
+  const int64_t left = a.T - k;
+  const int64_t n = c.n_prop[e];
+  return (int)(n < 0 ? 0 : (n > left ? left : n));
+}
 
 // ---------------------------------------------------------------------------------------------
 // cooperative, coalesced tile store (all threads of the CTA)
@@ -267,12 +353,20 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
     }
   }
   __syncthreads();  // prologue
+  PT_DECL();
   int64_t k = 0;
   for (int64_t e = 0; e < a.E; ++e) {
-    const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
+    const int n = epoch_steps3(a, c, e, k);
     for (int it = 0; it < n; ++it) {
       const int64_t kk = k + it;
+#if !ESKF_OPT_LATEACQ
+      PT_MARK(1);
       fx_slot_acquire(c.mbar, kk);  // the covariance warps are done with the record of step kk - 2
+      PT_MARK(0);
+#endif
+#if ESKF_OPT_LATEACQ
+      double fx[FX3_SIZE];  // (only the entries of rows 3:9 are ever touched: registers)
+#endif
       if (act && ESKF3_SCALAR_ON(it)) {
         const double* uo = sx + (SX3_RING + 8 * (int)(kk & 3)) * F;
         const double* un = sx + (SX3_RING + 8 * (int)((kk + 1) & 3)) * F;
@@ -285,6 +379,9 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
           acc[i] = un[(3 + i) * F];
         }
         const double dt = un[6 * F];
+#if ESKF_OPT_LATEACQ
+        jac_rows_ab(Rold, dt, om_old, acc_old, fx);
+#else
         {  // rows 3:9 of Fx (Filter.py:253-255) from the buffered R_WB_old / om_old / acc_old: this role has them
           double fx[FX3_SIZE];
           jac_rows_ab(Rold, dt, om_old, acc_old, fx);
@@ -292,6 +389,7 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
 #pragma unroll
           for (int j = FX3_AB / 2; j < FX3_MAIN / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
         }
+#endif
         imu_nominal_step(p, v, q, Rwb, dt, om_old, acc_old, om, acc, Rold);
         if (a.trace) trace_pvq(a.trace + ((c.f0 + lane) * a.T + kk) * NX, p, v, q);
         const int s = (int)((kk + 1) & 1);
@@ -304,14 +402,31 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
 #pragma unroll
         for (int i = 0; i < 3; ++i) sx[(SX3_V + 3 * s + i) * F] = v[i];
       }
+#if ESKF_OPT_LATEACQ
+      // The nominal step never reads the covariance: it is computed while the covariance warps still work on the record
+      // that occupies this slot (step kk - 2); only the store of the rows waits for the slot.
+      PT_MARK(1);
+      fx_slot_acquire(c.mbar, kk);
+      PT_MARK(0);
+      if (act && ESKF3_SCALAR_ON(it)) {
+        d2* dst = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
+#pragma unroll
+        for (int j = FX3_AB / 2; j < FX3_MAIN / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
+      }
+#endif
       fx_slot_publish(c.mbar, kk);  // rows 3:9 of the record of step kk are in place
+      PT_MARK(1);
       scalar_barrier();
+      PT_MARK(2);
     }
     k += n;
     if (!a.do_update) continue;
     scalar_barrier();  // (an update-only launch has no step barrier: the measurement must be staged before U0)
+    PT_MARK(2);
+    PT_MARK(5);
     __syncthreads();  // U0 | U1
     __syncthreads();  // U1 | U2
+    PT_MARK(3);
     if (act) {
       if (sx[SX3_OK2 * F] != 0.0) {  // state (+) error state, IMU part (state.py:46-53,116-121)
         const double th[3] = {sx[(SX3_DELTA + 6) * F], sx[(SX3_DELTA + 7) * F], sx[(SX3_DELTA + 8) * F]};
@@ -333,6 +448,15 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
 #pragma unroll
         for (int i = 0; i < 3; ++i) sx[(SX3_V + 3 * s + i) * F] = v[i];
       }
+#if ESKF_OPT_PP
+      if (a.snap) {  // statistics in the post-pass (eskf_pp.cuh): snapshot of this update
+        double* xs = a.snap + (e * a.N + c.f0 + lane) * 14;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) xs[i] = v[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xs[3 + i] = q[i];
+      } else
+#endif
       if (a.cam_ref && a.imu_ref) {  // statistics of this update are evaluated later, off the critical path
         double* xs = a.x + (c.f0 + lane) * NX;
 #pragma unroll
@@ -341,7 +465,9 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
         for (int i = 0; i < 4; ++i) xs[6 + i] = q[i];
       }
     }
+    PT_MARK(6);
     scalar_barrier();  // U2 of the scalar roles done (the covariance warps do not wait: see role3_cov)
+    PT_MARK(2);
   }
   // ---- write back ----
   if (act) {
@@ -390,12 +516,17 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
     st = a.status[c.f0 + lane];
   }
   __syncthreads();  // prologue
+  PT_DECL();
   int64_t k = 0;
   for (int64_t e = 0; e < a.E; ++e) {
-    const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
+    const int n = epoch_steps3(a, c, e, k);
     for (int it = 0; it < n; ++it) {
       const int64_t kk = k + it;
+#if !ESKF_OPT_LATEACQ
+      PT_MARK(1);
       fx_slot_acquire(c.mbar, kk);  // the covariance warps are done with the record of step kk - 2
+      PT_MARK(0);
+#endif
       if (act && ESKF3_SCALAR_ON(it)) {
         const double* uo = sx + (SX3_RING + 8 * (int)(kk & 3)) * F;
         const double* un = sx + (SX3_RING + 8 * (int)((kk + 1) & 3)) * F;
@@ -419,7 +550,12 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
         cam_nominal_step(pc, qc, vpre, Rwb, dt, om_old, om, pkp, pkR, pkz, notch_d);
         if (a.trace) trace_cam(a.trace + ((c.f0 + lane) * a.T + kk) * NX, pc, qc);
       }
-      pk_ready_wait();  // JACOB has published the probe kinematics of the post-predict (dofs, notch): PK slot sn, TR
+      PT_MARK(1);
+      pk_ready_wait();
+      PT_MARK(4);  // JACOB has published the probe kinematics of the post-predict (dofs, notch): PK slot sn, TR
+#if ESKF_OPT_LATEACQ
+      double fx[FX3_SIZE];  // (only the entries of rows 18:21 are ever touched: registers)
+#endif
       if (act && ESKF3_SCALAR_ON(it)) {
         // rows 18:21 of Fx (Filter._cam_error_jacobian, Filter.py:270-342): the half of the Jacobian work that
         // only needs the probe kinematics, R_WB_old and om_old -- taken off JACOB, the longest scalar role
@@ -435,18 +571,30 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
         }
 #pragma unroll
         for (int i = 0; i < 9; ++i) Ro[i] = sx[(SX3_RO + 9 * s + i) * F];
+#if ESKF_OPT_LATEACQ
+        jac_rows_h1(a.model, dofs, pk, trv, Ro, dt, om_old, sig_om, fx);
+      }
+      PT_MARK(1);
+      fx_slot_acquire(c.mbar, kk);  // (see role3_imu: only the store waits for the slot)
+      PT_MARK(0);
+      if (act && ESKF3_SCALAR_ON(it)) {
+#else
         double fx[FX3_SIZE];
         jac_rows_h1(a.model, dofs, pk, trv, Ro, dt, om_old, sig_om, fx);
+#endif
         d2* dst = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
 #pragma unroll
         for (int j = FX3_H1 / 2; j < FX3_AB / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
       }
       fx_slot_publish(c.mbar, kk);  // rows 18:21 of the record of step kk are in place
+      PT_MARK(1);
       scalar_barrier();
+      PT_MARK(2);
     }
     k += n;
     if (!a.do_update) continue;
     scalar_barrier();  // (an update-only launch has no step barrier: the measurement must be staged before U0)
+    PT_MARK(2);
     // ---- U0: residual (Filter.py:363-375) ----
     if (lane < F) {
       bool ok = false;
@@ -469,8 +617,12 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
       }
       sx[SX3_OK * F] = ok ? 1.0 : 0.0;
     }
+    PT_MARK(5);
+    PT_MARK(5);
     __syncthreads();  // U0 | U1
     __syncthreads();  // U1 | U2
+    PT_MARK(3);
+    PT_MARK(3);
     if (act) {
       if (sx[SX3_OK2 * F] != 0.0) {  // camera part of the injection, incl. the dqc axis slip (quirk Q4, state.py:124)
         const double th[3] = {sx[(SX3_DELTA + 6) * F], sx[(SX3_DELTA + 7) * F], sx[(SX3_DELTA + 8) * F]};
@@ -487,6 +639,15 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
       } else {
         st |= ESKF_STATUS_UPDATE_SKIPPED;
       }
+#if ESKF_OPT_PP
+      if (a.snap) {
+        double* xs = a.snap + (e * a.N + c.f0 + lane) * 14;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) xs[7 + i] = pc[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xs[10 + i] = qc[i];
+      } else
+#endif
       if (a.cam_ref && a.imu_ref) {  // statistics of this update are evaluated later, off the critical path
         double* xs = a.x + (c.f0 + lane) * NX;
 #pragma unroll
@@ -495,7 +656,9 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
         for (int i = 0; i < 4; ++i) xs[22 + i] = qc[i];
       }
     }
+    PT_MARK(6);
     scalar_barrier();  // U2 of the scalar roles done (the covariance warps do not wait: see role3_cov)
+    PT_MARK(2);
   }
   if (act) {
     double* xg = a.x + (c.f0 + lane) * NX;
@@ -548,14 +711,18 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
     put_notch(0, notch, dofs);
   }
   __syncthreads();  // prologue
+  PT_DECL();
   int64_t k = 0;
   for (int64_t e = 0; e < a.E; ++e) {
-    const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
+    const int n = epoch_steps3(a, c, e, k);
     for (int it = 0; it < n; ++it) {
       const int64_t kk = k + it;
+#if !ESKF_OPT_LATEACQ
+      PT_MARK(1);
       fx_slot_acquire(c.mbar, kk);  // the covariance warps are done with the record of step kk - 2
+      PT_MARK(0);
+#endif
       if (act && ESKF3_SCALAR_ON(it)) {
-        const double* uo = sx + (SX3_RING + 8 * (int)(kk & 3)) * F;
         const double dt = sx[(SX3_RING + 8 * (int)((kk + 1) & 3) + 6) * F];
         const int s = (int)(kk & 1), sn = s ^ 1;
         // post-predict (dofs, notch) and their probe kinematics -> PK slot of the next step
@@ -571,6 +738,37 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
         if (a.trace) trace_dofs(a.trace + ((c.f0 + lane) * a.T + kk) * NX, dofs, notch);
       }
       pk_ready_arrive();  // the CAMERA warp takes rows 18:21 from here
+#if ESKF_OPT_LATEACQ
+      double fx[FX3_SIZE];  // (rows 21:24 and, with IMU noise in Q, the noise rows: registers)
+      if (act && ESKF3_SCALAR_ON(it)) {
+        const double* uo = sx + (SX3_RING + 8 * (int)(kk & 3)) * F;
+        const double dt = sx[(SX3_RING + 8 * (int)((kk + 1) & 3) + 6) * F];
+        const int s = (int)(kk & 1), sn = s ^ 1;
+        const PKView<F> pk = pkv(sn);
+        double om_old[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) om_old[i] = uo[i * F];
+        jac_rows_h2(a.model, notch[1], pk, trv, dt, om_old, sig_om, fx);
+        if (imu_q) {
+          double Ro[9];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) Ro[i] = sx[(SX3_RO + 9 * s + i) * F];
+          jac_rows_noise(pk, Ro, dt, fx);
+        }
+      }
+      PT_MARK(1);
+      fx_slot_acquire(c.mbar, kk);  // (see role3_imu: only the store waits for the slot)
+      PT_MARK(0);
+      if (act && ESKF3_SCALAR_ON(it)) {
+        d2* dst = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
+#pragma unroll
+        for (int j = 0; j < FX3_H1 / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
+        if (imu_q) {
+#pragma unroll
+          for (int j = FX3_NPAIR_MAIN; j < FX3_NPAIR; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
+        }
+      }
+#else
       if (act && ESKF3_SCALAR_ON(it)) {
         const double* uo = sx + (SX3_RING + 8 * (int)(kk & 3)) * F;
         const double dt = sx[(SX3_RING + 8 * (int)((kk + 1) & 3) + 6) * F];
@@ -593,14 +791,20 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
           for (int j = FX3_NPAIR_MAIN; j < FX3_NPAIR; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
         }
       }
+#endif
       fx_slot_publish(c.mbar, kk);  // dt, rows 21:24 (and the noise rows) of the record of step kk are in place
+      PT_MARK(1);
       scalar_barrier();
+      PT_MARK(2);
     }
     k += n;
     if (!a.do_update) continue;
     scalar_barrier();  // (an update-only launch has no step barrier: the measurement must be staged before U0)
+    PT_MARK(2);
+    PT_MARK(5);
     __syncthreads();  // U0 | U1
     __syncthreads();  // U1 | U2
+    PT_MARK(3);
     if (act) {
       if (sx[SX3_OK2 * F] != 0.0) {
 #pragma unroll
@@ -613,7 +817,9 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
         if (a.trace && k > 0) trace_dofs(a.trace + ((c.f0 + lane) * a.T + k - 1) * NX, dofs, notch);
       }
     }
+    PT_MARK(6);
     scalar_barrier();  // U2 of the scalar roles done (the covariance warps do not wait: see role3_cov)
+    PT_MARK(2);
   }
   if (act) {
     double* xg = a.x + (c.f0 + lane) * NX;
@@ -639,14 +845,65 @@ __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int l
   const bool act = lane < c.nf;
   double* sx = c.smem + L::SX + lane;
   const int64_t gid = a.noise_mod > 0 ? (c.gid0 + lane) % a.noise_mod : c.gid0 + lane;  // id the noise is keyed by
+#if ESKF_OPT_PP
+  // pre-pass mode: the (noisy) samples of every filter were prepared by eskf_pp_streams_kernel -- same generator, same sums
+  const bool noisy = a.noise_on && !(a.noise_free0 && gid == 0) && !a.imu_pf;
+  const double* oap = a.imu_pf ? a.imu_pf + (c.f0 + lane) * 6
+                      : a.om_acc ? (a.stream_per_filter ? a.om_acc + (c.f0 + lane) * a.T * 6 : a.om_acc + c.traj * a.T * 6)
+                                 : nullptr;
+  const int64_t oas = a.imu_pf ? a.N * 6 : 6;  // doubles between consecutive samples of this lane's stream
+#else
   const bool noisy = a.noise_on && !(a.noise_free0 && gid == 0);
   const double* oap =
       a.om_acc ? (a.stream_per_filter ? a.om_acc + (c.f0 + lane) * a.T * 6 : a.om_acc + c.traj * a.T * 6) : nullptr;
+#endif
+#if ESKF_OPT_TMA
+  // chunk c = samples [c CH3_STEPS, (c + 1) CH3_STEPS) -> buffer c & 1; complete chunks only (the tail goes the plain way);
+  // needs the shared stream (one trajectory per CTA) and 16-byte aligned chunk sources
+  uint64_t* chbar = reinterpret_cast<uint64_t*>(c.smem + L::CHBAR);
+  double* chunk = c.smem + L::CHUNK;
+  const double* oa0 = a.om_acc ? a.om_acc + c.traj * a.T * 6 : nullptr;
+  const bool tma = oa0 && c.dtp && !a.stream_per_filter && ((reinterpret_cast<uintptr_t>(oa0) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(c.dtp) & 15) == 0);
+  const int64_t n_chunks = tma ? a.T / CH3_STEPS : 0;
+  // (lane 0 issues.  The buffer held chunk ch - 2, last read before the scalar barrier of the previous step: every lane
+  // of this warp has passed that barrier, so nobody still reads it)
+  auto issue_chunk = [&](int64_t ch) {
+    if (lane == 0 && ch < n_chunks) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      double* buf = chunk + (int)(ch & 1) * CH3_STEPS * 7;
+      mbar_expect_tx(chbar + (ch & 1), CH3_STEPS * 56);
+      bulk_g2s(buf, oa0 + ch * CH3_STEPS * 6, CH3_STEPS * 48, chbar + (ch & 1));
+      bulk_g2s(buf + CH3_STEPS * 6, c.dtp + ch * CH3_STEPS, CH3_STEPS * 8, chbar + (ch & 1));
+    }
+  };
+#endif
   auto stage_sample = [&](int64_t j) {  // sample of step j -> ring slot (j + 1) & 3
     double* dst = sx + (SX3_RING + 8 * (int)((j + 1) & 3)) * F;
     double u[6];
+#if ESKF_OPT_TMA
+    double dtj;
+    const int64_t ch = j / CH3_STEPS;
+    if (ch < n_chunks) {
+      const int jj = (int)(j - ch * CH3_STEPS);
+      if (jj == 0) issue_chunk(ch + 1);  // its buffer held chunk ch - 1: every lane is done with it
+      mbar_wait(chbar + (ch & 1), (uint32_t)((ch >> 1) & 1));
+      const double* buf = chunk + (int)(ch & 1) * CH3_STEPS * 7;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) u[i] = buf[jj * 6 + i];
+      dtj = buf[CH3_STEPS * 6 + jj];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) u[i] = oap[j * 6 + i];
+      dtj = c.dtp[j];
+    }
+#elif ESKF_OPT_PP
+#pragma unroll
+    for (int i = 0; i < 6; ++i) u[i] = oap[j * oas + i];
+#else
 #pragma unroll
     for (int i = 0; i < 6; ++i) u[i] = oap[j * 6 + i];
+#endif
     if (noisy) {
       double z[8];
       normal8(a.seed, (uint64_t)gid, (uint64_t)j, RNG_KIND_IMU, z);
@@ -655,9 +912,21 @@ __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int l
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) dst[i * F] = u[i];
+#if ESKF_OPT_TMA
+    dst[6 * F] = dtj;
+#else
     dst[6 * F] = c.dtp[j];
+#endif
   };
   auto stage_meas = [&](int64_t e) {
+#if ESKF_OPT_PP
+    if (a.meas_pf) {
+      const double* m = a.meas_pf + (e * a.N + c.f0 + lane) * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sx[(SX3_MEAS + i) * F] = m[i];
+      return;
+    }
+#endif
     const int64_t mrow = a.meas_per_filter ? (c.f0 + lane) : (c.traj * a.E + e);
     double cam[7];
 #pragma unroll
@@ -726,27 +995,47 @@ __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int l
 #pragma unroll
     for (int i = 0; i < 6; ++i) sx[(SX3_RING + i) * F] = ug[i];  // slot 0: the buffered previous sample
     sx[(SX3_RING + 6) * F] = 0.0;
-    if (a.T > 0 && oap) stage_sample(0);
   }
+#if ESKF_OPT_TMA
+  issue_chunk(0);
+#endif
+  if (act && a.T > 0 && oap) stage_sample(0);
   __syncthreads();  // prologue
+  PT_DECL();
   int64_t k = 0;
   for (int64_t e = 0; e < a.E; ++e) {
-    const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
+    const int n = epoch_steps3(a, c, e, k);
     if (act && a.do_update) stage_meas(e);
     const int fl = n < STATS_IT3 ? n : STATS_IT3;
     for (int it = 0;; ++it) {
+#if !ESKF_OPT_STATS_U0
       if (it == fl && act) flush_stats(e - 1);
+#endif
       if (it >= n) break;
       if (act && k + it + 1 < a.T && ESKF3_SCALAR_ON(it)) stage_sample(k + it + 1);
+      PT_MARK(1);
       scalar_barrier();
+      PT_MARK(2);
     }
     k += n;
     if (!a.do_update) continue;
     scalar_barrier();  // (an update-only launch has no step barrier: the measurement must be staged before U0)
+#if ESKF_OPT_STATS_U0
+    // error statistics of the PREVIOUS update, evaluated while the covariance warps form S, its inverse and the gain
+    // (~9,000 cycles during which every scalar role waits): the parked copies are only overwritten after U1 | U2
+    if (act) flush_stats(e - 1);
+    (void)fl;
+#endif
+    PT_MARK(5);
     __syncthreads();  // U0 | U1
     __syncthreads();  // U1 | U2
+    PT_MARK(3);
     scalar_barrier();  // U2 of the scalar roles done (the covariance warps do not wait: see role3_cov)
+#if ESKF_OPT_PP
+    pend = a.cam_ref && a.imu_ref && !a.snap;
+#else
     pend = a.cam_ref && a.imu_ref;
+#endif
   }
   if (act) {
     flush_stats(a.E - 1);
@@ -784,12 +1073,30 @@ __device__ __forceinline__ double rcp_nr(double x) {
 // shuffles per update).  Reads S from / writes inv(S) to the u3 record.  False for a singular or non-finite S
 // (the reference's LinAlgError branch, Filter.py:358-361).
 template <int QS>
-__device__ __forceinline__ bool inv7_group3(double* rec, int g) {
+__device__ __forceinline__ bool inv7_group3(double* rec, int g, const double* rd, int rds) {
   const unsigned FULL = 0xffffffffu;
   const int r = (g < 7) ? g : 6;  // lane 7 shadows row 6 and never becomes a pivot
   double a[7];
+#if ESKF_OPT_UPD
+  // row r of the tile's view of S straight from the H P record (upd3_publish_S): entries h_0..h_5 = 18..23 are three
+  // 16-byte pairs, h_6 = 15; the measurement noise goes on the diagonal here (the same sum as in the publishing lane)
+  {
+    const double rr = rd[r * rds];
+    double hp[6];
+#pragma unroll
+    for (int j = 0; j < 6; j += 2) {
+      const d2 t = reinterpret_cast<const d2*>(rec)[((U3_HP + 24 * r + 18 + j) >> 1) * QS];
+      hp[j] = t.x;
+      hp[j + 1] = t.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) a[j] = hp[j] + ((j == r) ? rr : 0.0);
+    a[6] = u3_get<QS>(rec, U3_HP + 24 * r + 15) + ((r == 6) ? rr : 0.0);
+  }
+#else
 #pragma unroll
   for (int j = 0; j < 7; ++j) a[j] = u3_get<QS>(rec, U3_S + 7 * r + j);
+#endif
   bool used = (g == 7);
   bool ok = true;
   int myk = 0;         // the row of inv(S) this lane ends up holding
@@ -846,6 +1153,15 @@ __device__ __forceinline__ bool inv7_group3(double* rec, int g) {
   return ((bal >> (lane & 24u)) & 0xffu) == 0xffu;
 }
 
+// warp-level synchronisation of the step loop: the eight lanes of a filter exchange their tiles through the filter's
+// buffer.  All 32 lanes of a covariance warp run the step loop together (nothing in it depends on the filter), so the
+// full-mask form is valid; the per-filter mask compiles into a MATCH / REDUX / BRA.DIV sequence of ~100 cycles.
+#if ESKF_OPT_SYNCW
+#define COV3_SYNCWARP() __syncwarp()
+#else
+#define COV3_SYNCWARP() __syncwarp(gmask)
+#endif
+
 template <int F, int NTHR>
 __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct) {
   using L = Lay3<F>;
@@ -895,11 +1211,21 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
   // ill-conditioned tuning makes large enough to matter.
   load_rows();
   __syncthreads();  // prologue
+  PT_DECL();
+#ifdef ESKF_EXP_STAGGER  // (profiling experiment: the second covariance warp of every sub-partition starts late)
+  if (ct >= 128) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < ESKF_EXP_STAGGER) {
+    }
+  }
+#endif
 
   int64_t k = 0;
   for (int64_t e = 0; e < a.E; ++e) {
-    const int n = c.n_prop ? c.n_prop[e] : (int)a.T;
+    const int n = epoch_steps3(a, c, e, k);
+    PT_MARK(15);
     if (n > 0) fx_slot_wait(c.mbar, k);  // the Jacobian record of the first step of the epoch is complete
+    PT_MARK(0);
     const int n_ex = ESKF3_COV_ON ? n + (n & 1) : n;  // (one exchange more after an odd number of propagations)
     for (int it = 0; it < n_ex; ++it) {
       const int64_t kk = k + it;
@@ -915,15 +1241,33 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
 #pragma unroll
             for (int v = 0; v < 3; ++v) Tb[i * RS3 + 3 * cg + v] = X[i][v];
         }
-        __syncwarp(gmask);
+        COV3_SYNCWARP();
+        PT_MARK(1);
+#if ESKF_OPT_STREAM
+        if (!step) {
+          load_rows();
+          COV3_SYNCWARP();
+          break;
+        }
+        // pass 2 fused with the transposed reload: P'(3g+v, :) = Fx T(3g+v, :)^T, T streamed from the buffer
+        fx3_apply_stream<F, RS3>(X, f2, Tb + 3 * cg * RS3);
+        PT_MARK(4);
+        // the record of the NEXT step: its producers stored it one step ago (ESKF_OPT_LATEACQ) -- normally no wait
+        if (it + 1 < n) fx_slot_wait(c.mbar, kk + 1);
+        COV3_SYNCWARP();  // every lane of the filter is done with the buffer before pass 1 of the next step stores
+        PT_MARK(3);
+#else
         load_rows();  // X[k][v] = T(3g+v, k) -- every lane, the identity rows 9:15 included (eskf_cov3.cuh)
+        PT_MARK(2);
         // the record of the NEXT step is waited for here, behind the latency of the transposed reload, so that
         // nothing stands between the end of this step and the first coefficient fetch of the next one
         if (it + 1 < n) fx_slot_wait(c.mbar, kk + 1);
-        __syncwarp(gmask);
+        COV3_SYNCWARP();
+        PT_MARK(3);
         if (!step) break;
         // pass 2: P'(3g+v, :) = Fx T(3g+v, :)^T
         fx3_apply_inplace<F>(X, f2);
+#endif
         // (the lane index is laundered through an empty asm so that the thirteen selected addends of the diagonal
         // are formed here, two selects each, instead of being hoisted out of the loop and spilled)
         int gl = cg;
@@ -933,6 +1277,7 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
 #endif
       }
       fx_slot_release(c.mbar, kk);  // this warp is done with the record
+      PT_MARK(4);
     }
     k += n;
     if (!a.do_update) continue;
@@ -948,8 +1293,10 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
     for (int m = 0; m < 7; ++m) rd[m] = sxc[(SX3_RD + m) * F];
     upd3_publish_S<4>(X, cg, rd, rec);
     __syncwarp(gmask);
-    const bool inv_ok = inv7_group3<4>(rec, cg);
+    const bool inv_ok = inv7_group3<4>(rec, cg, sxc + SX3_RD * F, F);
+    PT_MARK(5);
     __syncthreads();  // U0 | U1
+    PT_MARK(6);
     const bool upd_c = inv_ok && (sxc[SX3_OK * F] != 0.0);
     if (upd_c) {
       double K[3][7], res[7], dl[3];
@@ -966,17 +1313,26 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
       }
     }
     if (cg == 0) sxw[SX3_OK2 * F] = upd_c ? 1.0 : 0.0;
+    PT_MARK(7);
     __syncthreads();  // U1 | U2  (also orders the K / K R records of the eight lanes)
+    PT_MARK(8);
     if (upd_c) {
       upd3_w_pass<4>(X, cg, rec);
       __syncwarp(gmask);
+      PT_MARK(9);
+#if ESKF_OPT_UPD
+      upd3_finish<4, F, F>(X, cg, rec, sxc + SX3_RD * F, sxc + (SX3_DELTA + 6) * F, sxc + (SX3_DELTA + 21) * F);
+#else
       const double dth[3] = {sxc[(SX3_DELTA + 6) * F], sxc[(SX3_DELTA + 7) * F], sxc[(SX3_DELTA + 8) * F]};
       const double dthc[3] = {sxc[(SX3_DELTA + 21) * F], sxc[(SX3_DELTA + 22) * F], sxc[(SX3_DELTA + 23) * F]};
-      upd3_finish<4, F>(X, cg, rec, sxc + SX3_RD * F, dth, dthc);
+      upd3_finish<4, F, 1>(X, cg, rec, sxc + SX3_RD * F, dth, dthc);
+#endif
     }
+    PT_MARK(10);
     // no CTA barrier here: the scalar roles go on to the first steps of the next epoch while the covariance warps
     // finish the Joseph form (what they exchange next is ordered by the record pipeline and by the next U0 | U1)
   }
+  PT_FLUSH();
   dump_rows();
   __syncthreads();
   store_tiles3<F, NTHR>(a, c, threadIdx.x);
@@ -1003,6 +1359,11 @@ __global__ void __launch_bounds__(128 + 8 * F, 1) eskf_kernel3(const __grid_cons
     mbar_init(c.mbar + 1, 3);
     mbar_init(c.mbar + 2, F / 4);  // empty[s]: the covariance warps
     mbar_init(c.mbar + 3, F / 4);
+#if ESKF_OPT_TMA
+    mbar_init(reinterpret_cast<uint64_t*>(smem + L::CHBAR), 1);  // chunk[b]: one arrival (expect_tx) + the bytes of the copies
+    mbar_init(reinterpret_cast<uint64_t*>(smem + L::CHBAR) + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
   }
 
   // ---- covariance tiles and parameters (coalesced) ----
@@ -1019,6 +1380,8 @@ __global__ void __launch_bounds__(128 + 8 * F, 1) eskf_kernel3(const __grid_cons
   __syncthreads();
 
   const int warp = tid >> 5, lane = tid & 31;
+  // (setmaxnreg must be executed by all four warps of a warpgroup alike: the scalar roles are warps 0..3, one per SM
+  // sub-partition -- a remapping that put two scalar roles on the sub-partition with the single covariance warp hung)
   if (warp >= 4) {
     reg_inc3<REG_C>();
     role3_cov<F, NTHR>(a, c, tid - 128);

@@ -39,3 +39,16 @@ cudaError_t launch_eskf_kernel3<ESKF_F>(const KArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace eskf
+
+#if defined(ESKF_EXP_TIMING) && ESKF_F == 28
+// profiling build only: reads (and clears) the phase-cycle table [256 CTAs][12 warps][16 slots]
+extern "C" int eskf_debug_timing(long long* out) {
+  const size_t bytes = sizeof(long long) * 256 * 12 * TIMING_SLOTS;
+  cudaError_t e = cudaMemcpyFromSymbol(out, eskf::g_eskf_timing, bytes);
+  if (e != cudaSuccess) return -1;
+  void* p = nullptr;
+  cudaGetSymbolAddress(&p, eskf::g_eskf_timing);
+  cudaMemset(p, 0, bytes);
+  return 0;
+}
+#endif

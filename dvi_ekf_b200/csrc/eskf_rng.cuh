@@ -53,7 +53,9 @@ ESKF_HD void box_muller32(uint32_t a, uint32_t b, double* z) {
   const float u1 = (float)a * 2.3283064365386963e-10f + 1.1641532182693481e-10f;  // a 2^-32 + 2^-33
   const float th = (float)(int32_t)b * 1.4629180792671596e-9f;                     // b pi 2^-31
 #ifdef __CUDA_ARCH__
-  const float r = sqrtf(-2.0f * __logf(u1));
+  // (lg2.approx is only accurate to ~2^-22 absolute near 1: for u1 = 1 - 2^-24 the approximate logarithm may come out
+  // with the wrong sign; the clamp turns that one-in-2^24 NaN into r = 0 and changes nothing else)
+  const float r = sqrtf(fmaxf(0.0f, -2.0f * __logf(u1)));
   const float s = __sinf(th), c = __cosf(th);
 #else
   const float r = sqrtf(-2.0f * logf(u1));

@@ -120,6 +120,25 @@ void hc_propagate3(const double* model, double* x, double* P, double* u, double*
   if (fx_out) memcpy(fx_out, fx3, sizeof(double) * FX3_SIZE);
 }
 
+// Pass 2 of the covariance propagation both ways for one filter: reload + fx3_apply_inplace (out_a) and the streaming
+// pass fx3_apply_stream (out_b), from the same transposition buffer T[24][24] and fx3 record.  Both [8][24][3].
+void hc_pass2_both(const double* T, const double* fx3, double* out_a, double* out_b) {
+  alignas(16) double rec[FX3_SIZE];
+  alignas(16) double Tb[24 * 24];
+  memcpy(rec, fx3, sizeof(rec));
+  memcpy(Tb, T, sizeof(Tb));
+  const d2* f2 = reinterpret_cast<const d2*>(rec);
+  for (int g = 0; g < 8; ++g) {
+    double Xa[24][3], Xb[24][3];
+    fx3_load_transposed<24>(Xa, Tb + 3 * g * 24);
+    fx3_apply_inplace<1>(Xa, f2);
+    for (int i = 0; i < 24; ++i) for (int v = 0; v < 3; ++v) Xb[i][v] = -7.0;  // write-only operand: must be overwritten
+    fx3_apply_stream<1, 24>(Xb, f2, Tb + 3 * g * 24);
+    memcpy(out_a + g * 72, Xa, sizeof(Xa));
+    memcpy(out_b + g * 72, Xb, sizeof(Xb));
+  }
+}
+
 // Filter.update through the register-tile building blocks of eskf_kernel3.cuh: the eight lanes of a filter
 // replayed phase by phase around the u3 exchange record (warp-level synchronisation points = loop boundaries).
 int hc_update3(const double* model, double* x, double* P, const double* u, const double* Ro, const double* cam /*pos3 quat4*/,
@@ -133,6 +152,9 @@ int hc_update3(const double* model, double* x, double* P, const double* u, const
   alignas(16) double rec[U3_SIZE];
   for (int g = 0; g < 8; ++g) upd3_publish_S<1>(X[g], g, rd, rec);
   double S[49], Si[49];
+#if ESKF_OPT_UPD  // the tile's view of S comes from the H P record (inv7_group3): S^T(j, i) = H P(j, h_i) + [i == j] R_i
+  for (int i = 0; i < 7; ++i) for (int j = 0; j < 7; ++j) rec[U3_S + 7 * j + i] = rec[U3_HP + 24 * j + ESKF_HSET(i)] + ((i == j) ? rd[i] : 0.0);
+#endif
   for (int i = 0; i < 7; ++i) for (int j = 0; j < 7; ++j) S[7 * i + j] = rec[U3_S + 7 * j + i];  // the record holds S^T (eskf_cov3.cuh)
   bool ok = inv7(S, Si);
   for (int j = 0; j < 49; ++j) rec[U3_SINV + j] = Si[j];
@@ -147,7 +169,7 @@ int hc_update3(const double* model, double* x, double* P, const double* u, const
   }
   inject_error(m, s, delta);
   for (int g = 0; g < 8; ++g) upd3_w_pass<1>(X[g], g, rec);
-  for (int g = 0; g < 8; ++g) upd3_finish<1, 1>(X[g], g, rec, rd, delta + 6, delta + 21);
+  for (int g = 0; g < 8; ++g) upd3_finish<1, 1, 1>(X[g], g, rec, rd, delta + 6, delta + 21);
   for (int g = 0; g < 8; ++g)
     for (int i = 0; i < 24; ++i) for (int v = 0; v < 3; ++v) P[(3 * g + v) * 24 + i] = X[g][i][v];
   store_nominal(s, x, uu, RR);

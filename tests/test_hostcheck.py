@@ -237,3 +237,17 @@ def test_lockstep_random_tunings(hc, golden, fn, ufn):
                 wus, wuP = max(wus, state_err(x, xr)), max(wuP, cov_err(P, Pr, Rd))
     assert wps < TOL and wpP < TOL, (wps, wpP)
     assert wus < 1e-11 and wuP < 1e-11, (wus, wuP)
+
+
+def test_streaming_pass2_is_bit_identical(hc, golden):
+    """fx3_apply_stream (pass 2 fused with the transposed reload, eskf_cov3.cuh) performs the same operations in the same
+    order per accumulator as the reload followed by fx3_apply_inplace: identical bits on random tiles and records."""
+    hc.hc_pass2_both.argtypes = [dp, dp, dp, dp]
+    hc.hc_pass2_both.restype = None
+    rng = np.random.default_rng(11)
+    for _ in range(50):
+        T = rng.normal(size=(24, 24)) * 10.0 ** rng.integers(-6, 6, size=(24, 24))
+        fx3 = rng.normal(size=90)
+        a, b = np.empty((8, 24, 3)), np.empty((8, 24, 3))
+        hc.hc_pass2_both(_p(T), _p(fx3), _p(a), _p(b))
+        assert np.array_equal(a, b)

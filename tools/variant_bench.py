@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--fpc", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--stats", action="store_true", help="also time the launch with the error statistics on (what bench.py times)")
+    ap.add_argument("--digest", action="store_true", help="print a SHA-1 of the final (x, P, status) of the last timed launch: builds "
+                    "that only re-schedule the same arithmetic must agree bit for bit")
     a = ap.parse_args()
     wl = Workload()
     s = wl.s
@@ -46,14 +48,24 @@ def main():
                     kw = dict(imu_noise_std=wl.imu_std, cam_noise_std=wl.cam_std, seed=SEED) if noise else {}
                     e0.record()
                     if stats:
-                        bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], cam_ref=d["cam_ref"], imu_ref=d["imu_ref"],
-                               stats_on_device=True, **kw)
+                        ret = bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], cam_ref=d["cam_ref"], imu_ref=d["imu_ref"],
+                                     stats_on_device=True, **kw)
                     else:
                         bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], want_stats=False, **kw)
                     e1.record()
                     torch.cuda.synchronize()
                     best = min(best, e0.elapsed_time(e1))
-                print(f"variant={var} N={N} noise={noise} stats={stats}: {best:.3f} ms -> {N * len(s.dt) / best * 1e3:.3e} filter-steps/s",
+                dg = ""
+                if a.digest:
+                    import hashlib
+
+                    xs, Ps, _, _, sts = bf.get_state()
+                    dg = " digest=" + hashlib.sha1(xs.tobytes() + Ps.tobytes() + sts.tobytes()).hexdigest()[:12]
+                    dg += f" nonfinite={int((~np.isfinite(xs)).any(1).sum())}"
+                    if stats:
+                        dg += " stats=" + hashlib.sha1(ret[0].cpu().numpy().tobytes()).hexdigest()[:12]
+                        dg += " sum78=%.10e,%.10e" % tuple(ret[1].cpu().numpy()[7:9])
+                print(f"variant={var} N={N} noise={noise} stats={stats}: {best:.3f} ms -> {N * len(s.dt) / best * 1e3:.3e} filter-steps/s{dg}",
                       flush=True)
                 bf.close()
 
