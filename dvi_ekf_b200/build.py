@@ -18,7 +18,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libeskf_b200.so")
-SHAPES = (4, 8, 12, 16, 20, 24, 28)  # filters per CTA of eskf_kernel (v1); keep in sync with eskf_api.cu
+SHAPES = (4, 28)  # filters per CTA of eskf_kernel (v1, test / A-B variant only); keep in sync with eskf_api.cu
 SHAPES3 = (4, 8, 16, 28)  # filters per CTA of eskf_kernel3 (v3)
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

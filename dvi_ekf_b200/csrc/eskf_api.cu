@@ -15,7 +15,7 @@ using namespace eskf;
 
 namespace eskf {
 #define ESKF_DECL(F) template <> cudaError_t launch_eskf_kernel<F>(const KArgs& a, cudaStream_t stream);
-ESKF_DECL(4) ESKF_DECL(8) ESKF_DECL(12) ESKF_DECL(16) ESKF_DECL(20) ESKF_DECL(24) ESKF_DECL(28)
+ESKF_DECL(4) ESKF_DECL(28)
 #undef ESKF_DECL
 #define ESKF_DECL3(F) template <> cudaError_t launch_eskf_kernel3<F>(const KArgs& a, cudaStream_t stream);
 ESKF_DECL3(4) ESKF_DECL3(8) ESKF_DECL3(16) ESKF_DECL3(28)
@@ -276,6 +276,53 @@ __global__ void stats_final_kernel(const double* __restrict__ partial, int64_t n
   out[threadIdx.x] = a;
 }
 
+// Filter.Fx (24 x 24) and Filter.Fi (24 x 13) as the reference assembles them (Filter.py:249-342), from the fx3 record the
+// producer roles filed for the last IMU step of a launch (KArgs::fx_dump): the dense matrices the register-tile algebra of
+// eskf_cov3.cuh applies implicitly.
+__global__ void expand_jac_kernel(const double* __restrict__ rec, int64_t n, double* __restrict__ Fx, double* __restrict__ Fi) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  const double* r = rec + f * FX3_SIZE;
+  if (Fx) {
+    double* M = Fx + f * 576;
+    for (int i = 0; i < 576; ++i) M[i] = 0.0;
+    for (int i = 0; i < 24; ++i) M[i * 24 + i] = 1.0;
+    const double dt = r[FX3_DT];
+    for (int i = 0; i < 3; ++i) {
+      M[i * 24 + 3 + i] = dt;  // Filter.py:252
+      for (int k = 0; k < 3; ++k) {
+        M[(3 + i) * 24 + 6 + k] = r[FX3_AB + 6 * k + i];      // Filter.py:253
+        M[(6 + i) * 24 + 6 + k] = r[FX3_AB + 6 * k + 3 + i];  // Filter.py:255
+      }
+    }
+    M[15 * 24 + 16] += dt;  // notch chain, Filter.py:257-258
+    M[16 * 24 + 17] += dt;
+    // rows 18:24: Fx[18:24, 0:22] = jacobian (Filter.py:279-285: columns 0..21 are overwritten, 22 and 23 keep the identity)
+    for (int i = 18; i < 24; ++i)
+      for (int j = 0; j < 22; ++j) M[i * 24 + j] = 0.0;
+    for (int i = 0; i < 3; ++i) {
+      M[(18 + i) * 24 + 3 + i] = dt;
+      for (int k = 0; k < 9; ++k) M[(18 + i) * 24 + 6 + k] = r[FX3_H1 + 3 * k + i];
+      M[(18 + i) * 24 + 16 + i] = 1.0;  // the mis-aligned identity block (quirk Q3)
+      for (int k = 0; k < 7; ++k) {
+        const int col = (k < 3) ? 9 + k : (k == 3) ? 15 : 19 + (k - 4);
+        M[(21 + i) * 24 + col] = r[FX3_H2 + 3 * k + i];
+      }
+    }
+  }
+  if (Fi) {
+    double* M = Fi + f * 312;
+    for (int i = 0; i < 312; ++i) M[i] = 0.0;
+    for (int i = 0; i < 12; ++i) M[(3 + i) * 13 + i] = 1.0;  // Filter.py:262-263
+    M[17 * 13 + 12] = 1.0;
+    for (int i = 0; i < 3; ++i)
+      for (int k = 0; k < 3; ++k) {
+        M[(18 + i) * 13 + 3 + k] = r[FX3_NP + 3 * i + k];
+        M[(21 + i) * 13 + 3 + k] = r[FX3_NT + 3 * i + k];
+      }
+  }
+}
+
 thread_local std::string g_err;
 
 }  // namespace
@@ -297,6 +344,8 @@ struct eskf_handle {
   int fpc = 0;  // filters per CTA (0 = automatic)
   int variant = 0;  // 0 = default (eskf_kernel3), 1 = eskf_kernel (first version, kept for A/B measurements), 3 = eskf_kernel3
   int sm_count = 148;
+  double* fxrec = nullptr;  // [N][FX3_SIZE] Jacobian record of the last step (eskf_keep_jacobians), or nullptr
+  size_t pp_budget = 0;  // bytes the pre- / post-pass buffers of one eskf_run may take (0: everything inside the kernel)
 };
 
 #define CK(call)                                                  \
@@ -333,8 +382,8 @@ static int stage_in(eskf_t* h, int slot, const void* src, size_t bytes, int mem,
   return ESKF_OK;
 }
 
-// memory the pre- / post-pass buffers of one eskf_run may take (ESKF_B200_PP_MAX_BYTES; 0 switches the mode off and the
-// generator / the statistics run inside the persistent kernel as in round 1)
+// default of eskf_set_prepass_budget: memory the pre- / post-pass buffers of one eskf_run may take (ESKF_B200_PP_MAX_BYTES;
+// 0 switches the mode off and the generator / the statistics run inside the persistent kernel as in round 1)
 static size_t pp_budget_bytes() {
   static const size_t v = [] {
     const char* e = getenv("ESKF_B200_PP_MAX_BYTES");
@@ -343,7 +392,7 @@ static size_t pp_budget_bytes() {
   return v;
 }
 
-static const int kShapes1[] = {28, 24, 20, 16, 12, 8, 4};  // eskf_kernel  (v1)
+static const int kShapes1[] = {28, 4};  // eskf_kernel  (v1: the first correct path, kept as an A/B and test variant only)
 static const int kShapes3[] = {28, 16, 8, 4};              // eskf_kernel3
 
 static int kernel_of(const eskf_t* h) { return h->variant == 1 ? 1 : 3; }
@@ -355,7 +404,7 @@ static int kernel_of(const eskf_t* h) { return h->variant == 1 ? 1 : 3; }
 static int pick_fpc(const eskf_t* h, int64_t fpt, bool multi_traj) {
   auto fits = [&](int c) { return !multi_traj || (fpt % c) == 0; };
   const int* shapes = kernel_of(h) == 3 ? kShapes3 : kShapes1;
-  const int ns = kernel_of(h) == 3 ? 4 : 7;
+  const int ns = kernel_of(h) == 3 ? 4 : 2;
   if (h->fpc > 0) {
     for (int i = 0; i < ns; ++i)
       if (shapes[i] == h->fpc && fits(shapes[i])) return shapes[i];
@@ -391,11 +440,6 @@ static int launch(eskf_t* h, const KArgs& a, int64_t fpt, bool multi_traj) {
   } else {
     switch (fpc) {
       case 28: e = launch_eskf_kernel<28>(a, h->stream); break;
-      case 24: e = launch_eskf_kernel<24>(a, h->stream); break;
-      case 20: e = launch_eskf_kernel<20>(a, h->stream); break;
-      case 16: e = launch_eskf_kernel<16>(a, h->stream); break;
-      case 12: e = launch_eskf_kernel<12>(a, h->stream); break;
-      case 8: e = launch_eskf_kernel<8>(a, h->stream); break;
       case 4: e = launch_eskf_kernel<4>(a, h->stream); break;
       default:
         g_err = "filters_per_traj must be a multiple of 4 when several trajectories are stacked";
@@ -422,6 +466,7 @@ static void base_args(const eskf_t* h, KArgs& a) {
   a.model = h->model;
   a.n_traj = 1;
   a.filters_per_traj = h->N;
+  a.fx_dump = h->fxrec;
 }
 
 extern "C" {
@@ -460,6 +505,7 @@ static int create_alloc(eskf_t* h, const eskf_model_t* model, int64_t n_filters,
   int smc = 0;
   CK(cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, device));
   h->sm_count = smc > 0 ? smc : 148;
+  h->pp_budget = pp_budget_bytes();
   const size_t n = (size_t)n_filters;
   CK(cudaMalloc(&h->x, n * NX * sizeof(double)));
   CK(cudaMalloc(&h->P, n * 576 * sizeof(double)));
@@ -488,6 +534,7 @@ int eskf_destroy(eskf_t* h) {
   cudaFree(h->par);
   cudaFree(h->status);
   cudaFree(h->stats_sum_dev);
+  cudaFree(h->fxrec);
   for (int i = 0; i < N_STAGE; ++i)
     if (h->stage[i]) cudaFree(h->stage[i]);
   delete h;
@@ -726,7 +773,7 @@ int eskf_run(eskf_t* h, const eskf_streams_t* sp, double* stats_out, double* sta
   PPArgs pp;
   memset(&pp, 0, sizeof(pp));
 #if ESKF_OPT_PP
-  if (kernel_of(h) == 3 && pp_budget_bytes() > 0 && T > 0 && E > 0) {
+  if (kernel_of(h) == 3 && h->pp_budget > 0 && T > 0 && E > 0) {
     pp.N = h->N;
     pp.T = T;
     pp.E = E;
@@ -744,7 +791,7 @@ int eskf_run(eskf_t* h, const eskf_streams_t* sp, double* stats_out, double* sta
     const size_t b_imu = a.noise_on ? (size_t)h->N * T * 6 * sizeof(double) : 0;
     const size_t b_meas = a.noise_on ? (size_t)h->N * E * 8 * sizeof(double) : 0;
     const size_t b_snap = want_stats ? (size_t)h->N * E * 14 * sizeof(double) : 0;
-    if (b_imu + b_meas + b_snap <= pp_budget_bytes()) {
+    if (b_imu + b_meas + b_snap <= h->pp_budget) {
       if (a.noise_on) {
         if ((rc = stage_reserve(h, 9, b_imu))) return rc;
         if ((rc = stage_reserve(h, 10, b_meas))) return rc;
@@ -883,6 +930,57 @@ int64_t eskf_launch_count(const eskf_t* h) { return h ? h->launches : 0; }
 int eskf_set_variant(eskf_t* h, int variant) {
   if (!h || (variant != 0 && variant != 1 && variant != 3)) return ESKF_EINVAL;
   h->variant = variant;
+  return ESKF_OK;
+}
+
+int eskf_keep_jacobians(eskf_t* h, int on) {
+  if (!h) return ESKF_EINVAL;
+  CK(cudaSetDevice(h->device));
+  if (on && !h->fxrec) {
+    CK(cudaMalloc(&h->fxrec, (size_t)h->N * FX3_SIZE * sizeof(double)));
+    CK(cudaMemsetAsync(h->fxrec, 0, (size_t)h->N * FX3_SIZE * sizeof(double), h->stream));
+  } else if (!on && h->fxrec) {
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaFree(h->fxrec));
+    h->fxrec = nullptr;
+  }
+  return ESKF_OK;
+}
+
+int eskf_get_jacobians(eskf_t* h, double* Fx, double* Fi, int mem) {
+  if (!h) return ESKF_EINVAL;
+  if (!h->fxrec || kernel_of(h) != 3) {
+    g_err = "eskf_get_jacobians: call eskf_keep_jacobians(h, 1) before the propagation (default kernel only)";
+    return ESKF_EINVAL;
+  }
+  CK(cudaSetDevice(h->device));
+  const size_t bx = (size_t)h->N * 576 * sizeof(double), bi = (size_t)h->N * 312 * sizeof(double);
+  double *dFx = Fx, *dFi = Fi;
+  int rc;
+  if (mem == ESKF_MEM_HOST) {
+    if (Fx) {
+      if ((rc = stage_reserve(h, 2, bx))) return rc;
+      dFx = (double*)h->stage[2];
+    }
+    if (Fi) {
+      if ((rc = stage_reserve(h, 3, bi))) return rc;
+      dFi = (double*)h->stage[3];
+    }
+  }
+  expand_jac_kernel<<<(unsigned)((h->N + 127) / 128), 128, 0, h->stream>>>(h->fxrec, h->N, dFx, dFi);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  if (mem == ESKF_MEM_HOST) {
+    if (Fx) CK(cudaMemcpyAsync(Fx, dFx, bx, cudaMemcpyDeviceToHost, h->stream));
+    if (Fi) CK(cudaMemcpyAsync(Fi, dFi, bi, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return ESKF_OK;
+}
+
+int eskf_set_prepass_budget(eskf_t* h, int64_t bytes) {
+  if (!h || bytes < 0) return ESKF_EINVAL;
+  h->pp_budget = (size_t)bytes;
   return ESKF_OK;
 }
 

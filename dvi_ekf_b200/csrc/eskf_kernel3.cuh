@@ -62,6 +62,9 @@
 #ifndef ESKF_OPT_PP
 #define ESKF_OPT_PP 1  // per-filter streams from a pre-pass and statistics in a post-pass (KArgs::imu_pf / meas_pf / snap)
 #endif
+#ifndef ESKF_OPT_JACDUMP
+#define ESKF_OPT_JACDUMP 1  // the producers file the Jacobian record of the last step of a launch (KArgs::fx_dump)
+#endif
 #ifndef ESKF_OPT_TMA
 #define ESKF_OPT_TMA 0  // sample stream staged by cp.async.bulk chunks (see CH3_STEPS)
 #endif
@@ -388,6 +391,13 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
           d2* dst = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
 #pragma unroll
           for (int j = FX3_AB / 2; j < FX3_MAIN / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
+#if ESKF_OPT_JACDUMP
+          if (a.fx_dump && kk == a.T - 1) {  // Filter.Fx / Filter.Fi read-out: the record of the last step of the launch
+            double* fd = a.fx_dump + (c.f0 + lane) * FX3_SIZE;
+#pragma unroll
+            for (int j = FX3_AB; j < FX3_MAIN; ++j) fd[j] = fx[j];
+          }
+#endif
         }
 #endif
         imu_nominal_step(p, v, q, Rwb, dt, om_old, acc_old, om, acc, Rold);
@@ -585,6 +595,13 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
         d2* dst = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
 #pragma unroll
         for (int j = FX3_H1 / 2; j < FX3_AB / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
+#if ESKF_OPT_JACDUMP
+        if (a.fx_dump && kk == a.T - 1) {
+          double* fd = a.fx_dump + (c.f0 + lane) * FX3_SIZE;
+#pragma unroll
+          for (int j = FX3_H1; j < FX3_AB; ++j) fd[j] = fx[j];
+        }
+#endif
       }
       fx_slot_publish(c.mbar, kk);  // rows 18:21 of the record of step kk are in place
       PT_MARK(1);
@@ -790,6 +807,21 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
 #pragma unroll
           for (int j = FX3_NPAIR_MAIN; j < FX3_NPAIR; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
         }
+#if ESKF_OPT_JACDUMP
+        if (a.fx_dump && kk == a.T - 1) {  // (rows 18:24 of Fi are part of the read-out whether or not Q uses them)
+          double* fd = a.fx_dump + (c.f0 + lane) * FX3_SIZE;
+          if (!imu_q) {
+            double Ro[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Ro[i] = sx[(SX3_RO + 9 * s + i) * F];
+            jac_rows_noise(pk, Ro, dt, fx);
+          }
+#pragma unroll
+          for (int j = 0; j < FX3_H1; ++j) fd[j] = fx[j];
+#pragma unroll
+          for (int j = FX3_MAIN; j < FX3_SIZE; ++j) fd[j] = fx[j];
+        }
+#endif
       }
 #endif
       fx_slot_publish(c.mbar, kk);  // dt, rows 21:24 (and the noise rows) of the record of step kk are in place

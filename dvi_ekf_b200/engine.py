@@ -252,6 +252,23 @@ class BatchFilter:
     def set_tuning(self, filters_per_cta: int = 0):
         check(self._lib.eskf_set_tuning(self._h, int(filters_per_cta)), "eskf_set_tuning")
 
+    def keep_jacobians(self, on: bool = True):
+        """The kernels file the Jacobian record of the last IMU step of every ``propagate`` / ``run`` (eskf_keep_jacobians)."""
+        check(self._lib.eskf_keep_jacobians(self._h, 1 if on else 0), "eskf_keep_jacobians")
+
+    def get_jacobians(self):
+        """``Filter.Fx`` [N,24,24] and ``Filter.Fi`` [N,24,13] of the last IMU step (Filter.py:249-342), dense, as numpy
+        arrays; needs ``keep_jacobians()`` before the propagation."""
+        Fx, Fi = np.empty((self.n, 24, 24)), np.empty((self.n, 24, 13))
+        check(self._lib.eskf_get_jacobians(self._h, Fx.ctypes.data_as(C.c_void_p), Fi.ctypes.data_as(C.c_void_p), MEM_HOST),
+              "eskf_get_jacobians")
+        return Fx, Fi
+
+    def set_prepass_budget(self, n_bytes: int):
+        """Memory ``run`` may use to keep the Monte-Carlo generator and the update-MSE statistics out of the persistent kernel
+        (include/eskf.h, eskf_set_prepass_budget); 0 = everything inside the kernel.  Both ways give the same bits."""
+        check(self._lib.eskf_set_prepass_budget(self._h, int(n_bytes)), "eskf_set_prepass_budget")
+
     def set_variant(self, variant: int = 0):
         """0 = default kernel (warp-specialised eskf_kernel3), 1 = first kernel (eskf_kernel), 3 = eskf_kernel3."""
         check(self._lib.eskf_set_variant(self._h, int(variant)), "eskf_set_variant")

@@ -148,8 +148,8 @@ class Filter:
         self.H = np.zeros([self.num_meas, 24])
         self.H[0:6, 18:24] = np.eye(6)
         self.H[6, 15] = 1
-        self.Fx = None  # the Jacobians stay on-chip; not materialised by the engine
-        self.Fi = None
+        self._engine.keep_jacobians(True)  # Fx / Fi of the last IMU step are read out on demand (properties below)
+        self._propagated = False
         self.traj = FilterTraj("kf")
         self.update_noise_matrices()  # with _dt = 0: Q[0:6] = 0 (Filter.py:40,68-72)
         self._engine.set_state(sim.x0.as_vector()[None], sim.cov0[None], sim.streams.u0[None], None)
@@ -158,6 +158,17 @@ class Filter:
         self.update_mse = 0
 
     # ---- state views -------------------------------------------------------
+    @property
+    def Fx(self):
+        """Filter.py:249-259: the error-state transition matrix of the last propagate (None before the first one, as in
+        the reference, which creates the attribute there)."""
+        return self._engine.get_jacobians()[0][0] if self._propagated else None
+
+    @property
+    def Fi(self):
+        """Filter.py:261-268: the noise Jacobian of the last propagate."""
+        return self._engine.get_jacobians()[1][0] if self._propagated else None
+
     @property
     def _states(self) -> State:
         return State.from_vector(self._engine.get_state()[0][0])
@@ -198,15 +209,34 @@ class Filter:
 
     # ---- Filter.py:144-230 -------------------------------------------------------
     def run(self, camera: Camera, k: int, run_desc_str: str = "") -> None:
+        """Filter.run (Filter.py:144-168): every epoch of the camera trajectory, as ONE launch of the persistent kernel in
+        trace mode (eskf_streams_t.trace_x: the nominal state after every IMU step, the updated state at the update
+        instants -- the rows FilterTraj keeps).  ``camera`` must be the simulator's camera (the streams were built from
+        it); epoch-by-epoch stepping with another camera goes through ``run_one_epoch``."""
         self.run_id = k
         s = self._sim.streams
-        kk = 0
-        for e in range(len(s.n_prop)):
-            self._propagate_range(kk, int(s.n_prop[e]))
-            kk += int(s.n_prop[e])
-            cam_meas = camera_at_index(camera, e + 1)
-            self.update(s.t_cam[e + 1], cam_meas, camera.get_notch_vec_at(e + 1)[0])
-            self.calculate_update_mse(e + 1, camera)
+        if camera is not self._sim.camera:  # a foreign camera object: the reference's loop, one launch per call
+            old_t = self._config.min_t
+            for i, t in enumerate(camera.t[1:]):
+                self.run_one_epoch(old_t, t, i + 1, camera)
+                self.calculate_update_mse(i + 1, camera)
+                old_t = t
+            return
+        T, E = len(s.dt), len(s.n_prop)
+        trace = np.zeros((1, T, 26))
+        st, _ = self._engine.run(s.dt, s.om_acc, s.n_prop, s.cam, s.notch, cam_ref=s.cam_ref, imu_ref=s.imu_ref,
+                                 gt_dofs=self._config.gt_imu_dofs, trace=trace)
+        for kk in range(T):
+            self.imu.ref_rows.append(s.imu_ref_rows[kk])
+            self.traj.append_propagated_states(s.t_imu[kk], State.from_vector(trace[0, kk]))
+        if T:
+            self._dt = float(s.dt[T - 1])
+            self.imu.om, self.imu.acc = s.om_acc[T - 1, :3].copy(), s.om_acc[T - 1, 3:].copy()
+            self._propagated = True
+        if int(st[0, 9]) != E:  # Filter.py:358-361: the reference prints and carries on with the next epoch
+            print("ERROR: Singular matrix!")
+            print("Stopping simulation.")
+        self.update_mse = float(st[0, 7])  # Filter.calculate_update_mse of the last epoch (Filter.py:397-418)
 
     def run_one_epoch(self, old_t: float, t: float, i_cam: int, camera: Camera) -> None:
         self.propagate_imu(old_t, t)
@@ -229,15 +259,23 @@ class Filter:
         """One IMU step with the current ``self._dt`` (Filter.py:219-230)."""
         oa = np.hstack((np.asarray(om, dtype=float).reshape(3), np.asarray(acc, dtype=float).reshape(3)))
         self._engine.propagate(np.array([self._dt]), oa[None])
+        self._propagated = True
         self.imu.om, self.imu.acc = oa[:3].copy(), oa[3:].copy()
         self.traj.append_propagated_states(t, self._states)
 
     # ---- Filter.py:351-395 ---------------------------------------------------------
     def update(self, t: float, camera: VisualMeasurementPoint, ang_notch: float):
+        st0 = int(self._engine.get_state()[4][0])
         K = self._engine.update(np.hstack((camera.pos, camera.q.xyzw)), float(ang_notch), want_gain=True)
-        st = int(self._engine.get_state()[4][0])
-        if st & 1:
-            print("ERROR: Singular matrix!")
+        # decided from THIS call (the engine's status word is sticky until the next reset): a skipped update leaves the
+        # gain buffer at zero
+        if not np.any(K[0]):
+            st = int(self._engine.get_state()[4][0])
+            if (st & ~st0) & 2 or ((st & 2) and not (st & 1)):
+                # math.asin raises ValueError in the reference (Quaternion.py:150-160) -- reported, not raised, here
+                print("ERROR: rotation residual outside the domain of asin!")
+            else:
+                print("ERROR: Singular matrix!")  # Filter.py:358-361
             print("Stopping simulation.")
             return None
         self.traj.append_updated_states(t, self._states)
@@ -417,10 +455,18 @@ class Simulator:
                             gt_dofs=cfg.gt_imu_dofs, seed=b.seed, imu_noise_std=imu_std, cam_noise_std=cam_std)
             self.final_states = bf.get_state()[0]
         self.stats = st
-        self.mses = [float(v) for v in st[:, 6]]  # DOF MSE of every run (Filter.calculate_dof_metric)
-        self.mse_best = min(self.mses)
+        # Simulator.py:138-158 appends ``kf.mse`` of every run -- which is 0 at the reference's HEAD, because the call that
+        # would set it is commented out (Filter.py:92,167-168).  ``mses`` / ``mse_best`` / ``mse_avg`` keep exactly that
+        # behaviour; the DOF metric the author meant (Filter.calculate_dof_metric, Filter.py:452-455) of every run is in
+        # ``dof_mses`` / ``dof_mse_best`` / ``dof_mse_avg`` ("Deviations").
+        self.mses = [float(self.kf.mse)] * n
+        self.mse_best = min(self.mse_best, min(self.mses))
         self.mse_avg = sum(self.mses) / len(self.mses)
+        self.dof_mses = [float(v) for v in st[:, 6]]
+        self.dof_mse_best = min(self.dof_mses)
+        self.dof_mse_avg = sum(self.dof_mses) / len(self.dof_mses)
         if verbose:
             print(f"\tOptimvars: {self.optim_std}")
             print(f"\tDOF MSE: {self.mse_avg:.2E}")
+            print(f"\tDOF MSE (Filter.calculate_dof_metric, mean of {n} runs): {self.dof_mse_avg:.2E}")
         return st, sm

@@ -45,9 +45,13 @@ def allreduce_stats(stats_sum, group=None):
 
 
 def summarise_stats(stats_sum):
-    """Error statistics of the whole job from the reduced vector (include/eskf.h: [0:6] sum (dofs - gt)^2, [7] sum of the
-    last update_mse, [9] applied updates, [11] filter count)."""
+    """Error statistics of the whole job from the reduced vector (include/eskf.h): sums over the HEALTHY filters (finite
+    row, status 0) in [0:10] -- [0:6] (dofs - gt)^2, [6] DOF metric, [7] last update_mse, [8] update_mse summed over the
+    epochs, [9] applied updates -- and the counts [10] filters with a non-zero status word, [11] healthy filters (the
+    divisor of every mean), [12] filters with non-finite results."""
     s = np.asarray(stats_sum, dtype=float)
     n = s[11]
-    return {"dof_rmse": [float(np.sqrt(v / n)) for v in s[:6]], "dof_metric_mean": float(s[6] / n),
-            "mean_update_mse_last": float(s[7] / n), "filters": float(n), "updates_applied": float(s[9])}
+    d = n if n > 0 else float("nan")
+    return {"dof_rmse": [float(np.sqrt(v / d)) for v in s[:6]], "dof_metric_mean": float(s[6] / d),
+            "mean_update_mse_last": float(s[7] / d), "filters": float(n), "updates_applied": float(s[9]),
+            "filters_flagged": float(s[10]), "filters_nonfinite": float(s[12])}

@@ -91,7 +91,12 @@ typedef struct {
 #define ESKF_NSTAT 16
 /* per-filter statistics row written by eskf_run: [0:6] (dofs - gt)^2, [6] dof metric (Filter.py:452-455),
  * [7] update_mse of the last epoch (Filter.py:397-418), [8] sum of update_mse over epochs,
- * [9] number of applied updates, [10] status, [11:16] reserved */
+ * [9] number of applied updates, [10] status word, [11] 1, [12:16] reserved.
+ * stats_sum (the vector a multi-GPU launcher all-reduces) is reduced from the rows after the launch, deterministically
+ * (fixed tree, no atomics) and MASKED: [0:10] sum the rows of the HEALTHY filters only (all of [0:10] finite and status
+ * word 0), [10] = number of filters with a non-zero status word, [11] = number of healthy filters (the divisor of every
+ * mean), [12] = number of filters with a non-finite row, [13:16] reserved (0).  A diverged filter therefore shows up in
+ * the counts and never turns the reduced vector into NaN. */
 
 /* Simulator.__init__ / Filter.__init__ (Simulator.py:30-68, Filter.py:34-93) */
 int eskf_create(const eskf_model_t* model, int64_t n_filters, int device, void* cuda_stream, eskf_t** out);
@@ -123,6 +128,13 @@ int eskf_run(eskf_t* h, const eskf_streams_t* streams, double* stats_out, double
 /* Filter._states / _P / buffers read-back.  Any pointer may be NULL. */
 int eskf_get_state(eskf_t* h, double* x, double* P, double* u_old, double* R_old, int32_t* status, int mem);
 
+/* Filter.Fx / Filter.Fi (Filter.py:249-268; the reference sets both on every propagate): after eskf_keep_jacobians(h, 1)
+ * the kernels file the Jacobian record of the LAST IMU step of every eskf_propagate / eskf_run launch (720 B per filter),
+ * and eskf_get_jacobians expands it into the dense matrices the reference holds: Fx [N,24,24], Fi [N,24,13]; either
+ * pointer may be NULL.  Default kernel only. */
+int eskf_keep_jacobians(eskf_t* h, int on);
+int eskf_get_jacobians(eskf_t* h, double* Fx, double* Fi, int mem);
+
 /* blocks until everything queued on the handle's stream has finished */
 int eskf_sync(eskf_t* h);
 
@@ -130,6 +142,12 @@ int eskf_sync(eskf_t* h);
 int64_t eskf_launch_count(const eskf_t* h);
 /* filters per CTA used for the kernels (tunable; 0 = automatic) */
 int eskf_set_tuning(eskf_t* h, int filters_per_cta);
+/* eskf_run keeps the Monte-Carlo generator and the update-MSE statistics OUT of the persistent kernel when their buffers
+ * fit this budget: a pre-pass kernel writes the noisy per-filter sample streams ([T,N,6] + [E,N,8] doubles), the
+ * persistent kernel leaves a 14-double snapshot per filter and update ([E,N,14]) and a post-pass evaluates the Euler
+ * angles of Filter.calculate_update_mse (Filter.py:397-418) from them.  Same generator, same operations: bit-identical to
+ * the in-kernel path (bytes = 0), which serves the sizes that do not fit.  Default: 32 GiB or ESKF_B200_PP_MAX_BYTES. */
+int eskf_set_prepass_budget(eskf_t* h, int64_t bytes);
 /* kernel variant: 0 = default (the warp-specialised eskf_kernel3), 1 = eskf_kernel (first version, kept for
  * A/B measurements), 3 = eskf_kernel3 */
 int eskf_set_variant(eskf_t* h, int variant);

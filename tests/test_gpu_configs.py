@@ -55,7 +55,7 @@ def test_config3_tuning_sweep_per_filter_q_r_p0(golden, variant):
     assert np.abs(xg[0] - xg[35]).max() > 1e-9  # the tuning really changes the estimate
 
 
-@pytest.mark.parametrize("variant,fpt", [(3, 8), (3, 28), (1, 12)])
+@pytest.mark.parametrize("variant,fpt", [(3, 8), (3, 28), (1, 12)])  # (v1 has the shapes 28 and 4: fpt 12 runs on 4)
 def test_config4_stacked_trajectories_33_samples_per_frame(golden, variant, fpt):
     from dvi_ekf_b200 import BatchFilter
 
