@@ -235,6 +235,167 @@ def ncu_traffic():
     return None
 
 
+def _timed(fn, reset, reps, barrier, flush):
+    """mean device time [ms] of `reps` calls of fn (CUDA events on torch's current stream, which is the handle's stream);
+    one untimed warm-up call; `reset` (state reload) and the L2 flush sit outside the events"""
+    import torch
+
+    reset()
+    fn()
+    barrier()
+    ms = []
+    for _ in range(reps):
+        reset()
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        barrier()
+        ms.append(e0.elapsed_time(e1))
+    return float(np.mean(ms)), out
+
+
+def secondary_workloads(a, wl, dev, local, rank, world, dist, flush, barrier):
+    """BASELINE.json configs 3, 4, 5 and the calibration (all DOFs estimated) variant of config 2, timed in the same run
+    as the headline, with the same clock sampler running.  Every rank works on its shard; the figures are max-over-ranks
+    device times.  Returns {name: {...}} on every rank (identical after the MAX all-reduce of the times)."""
+    import torch
+
+    from dvi_ekf_b200 import BatchFilter
+    from dvi_ekf_b200.prepass import build_streams_gpu
+    from dvi_ekf_b200.sharding import allreduce_stats, shard_of, summarise_stats
+
+    sc = wl.s
+    T, E = len(sc.dt), len(sc.n_prop)
+    t64 = lambda x, dtype=torch.float64: torch.tensor(np.ascontiguousarray(x), dtype=dtype, device=dev)
+    d = dict(dt=t64(sc.dt), oa=t64(sc.om_acc), npr=t64(sc.n_prop, torch.int32), cam=t64(sc.cam), notch=t64(sc.notch),
+             cam_ref=t64(sc.cam_ref), imu_ref=t64(sc.imu_ref))
+    P0, u0 = t64(wl.P0[None]), t64(sc.u0[None])
+    out = {}
+
+    def record(name, ms, n_total, steps_per_filter, ifv, scaling, what, stats=None, reps=0):
+        if dist is not None:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt[0])
+        fs = float(n_total) * steps_per_filter
+        out[name] = {"workload": what, "filters_total": int(n_total), "filter_steps_per_pass": fs, "ms_per_pass": ms,
+                     "value": fs / (ms * 1e-3), "unit": UNIT, "scaling": scaling, "timed_passes": reps,
+                     "flops_per_filter_step": 9031 + 29587 / ifv}
+        if stats is not None:
+            out[name]["stats"] = stats
+
+    # ---- config 3: 16^4 tuning grid, per-filter Q / R, noise-free streams (Simulator.py:163-245, config.yaml:76-82) ----
+    g = 16
+    n3 = g ** 4
+    first, cnt = shard_of(n3, rank, world)
+    ga, gb, gc, gd = np.meshgrid(np.logspace(-2, 2, g), np.logspace(-2, 2, g), np.logspace(-3, 3, g), np.logspace(-3, 3, g),
+                                 indexing="ij")
+    sl = slice(first, first + cnt)
+    ga, gb, gc, gd = ga.ravel()[sl], gb.ravel()[sl], gc.ravel()[sl], gd.ravel()[sl]
+    Qd = np.repeat(wl.Qd[None], cnt, 0)
+    Qd[:, 6:9] *= gb[:, None] ** 2
+    Qd[:, 9:12] *= ga[:, None] ** 2
+    Rd = np.repeat(wl.Rd[None], cnt, 0)
+    Rd[:, 0:3] *= gc[:, None] ** 2
+    Rd[:, 3:6] *= gd[:, None] ** 2
+    x0 = t64(sc.x0[None])
+    with BatchFilter(cnt, device=local, **wl.model) as bf:
+        bf.set_noise(Qd, Rd, wl.sig_om[None])
+
+        def run3():
+            st, sm = bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], cam_ref=d["cam_ref"], imu_ref=d["imu_ref"],
+                            stats_on_device=True, filter_id0=first)
+            allreduce_stats(sm)
+            return sm
+
+        ms, sm = _timed(run3, lambda: bf.set_state(x0, P0, u0, None), 3, barrier, flush)
+    record("config3", ms, n3, T, IFV, "strong", f"{n3}-filter tuning grid (16^4 over DOF random walks and camera measurement "
+           f"noise, per-filter Q / R), noise-free streams, mandala0_mono {N_FRAMES} frames x {IFV}; sharded over {world} GPU(s), "
+           "all-reduce of the statistics inside", summarise_stats(sm.cpu().numpy()), 3)
+
+    # ---- config 4: nine data/trajs trajectories x 1024 seeds, 33 IMU samples per frame, 200 frames, device pre-pass ----
+    from dvi_ekf_b200.camera import load_trajectory
+
+    names = ["mandala0_mono", "mandala0_gt", "trans_x", "trans_y", "trans_z", "rot_x", "rot_y", "rot_z", "from_prop"]
+    base, ifv4, frames, seeds_total = 50, 33, 200, 1024
+    seeds = seeds_total // world  # every rank: all nine trajectories x its share of the seeds
+    idx = np.resize(np.concatenate((np.arange(base), np.arange(base - 2, 0, -1))), frames)  # there and back again
+    tt = np.arange(frames) / 30.0
+    ds = []
+    for nm in names:
+        t_, xyz, q = load_trajectory(nm, max_vals=base)
+        ds.append(build_streams_gpu(tt, xyz[idx].copy(), q[idx].copy(), ifv4, wl.cfg.model.length, wl.cfg.model.angle,
+                                    scale=wl.cfg.camera.scale, device=local))
+    T4, E4 = ds[0].n_steps, frames - 1
+    cat = lambda f: torch.cat([f(x) for x in ds]).contiguous()
+    w = dict(dt=cat(lambda x: x.dt[:T4]), oa=cat(lambda x: x.om_acc[:T4]), npr=cat(lambda x: x.n_prop), cam=cat(lambda x: x.cam),
+             notch=cat(lambda x: x.notch), cam_ref=cat(lambda x: x.cam_ref), imu_ref=cat(lambda x: x.imu_ref),
+             x0=torch.cat([x.x0[None].repeat(seeds, 1) for x in ds]).contiguous(),
+             u0=torch.cat([x.u0[None].repeat(seeds, 1) for x in ds]).contiguous())
+    n4 = len(names) * seeds
+    with BatchFilter(n4, device=local, **wl.model) as bf:
+        bf.set_noise(wl.Qd[None], wl.Rd[None], wl.sig_om[None])
+
+        def run4():
+            st, sm = bf.run(w["dt"], w["oa"], w["npr"], w["cam"], w["notch"], cam_ref=w["cam_ref"], imu_ref=w["imu_ref"],
+                            n_traj=len(names), filters_per_traj=seeds, stats_on_device=True, seed=SEED,
+                            filter_id0=rank * n4, imu_noise_std=wl.imu_std, cam_noise_std=wl.cam_std)
+            allreduce_stats(sm)
+            return sm
+
+        ms, sm = _timed(run4, lambda: bf.set_state(w["x0"], P0, w["u0"], None), 3, barrier, flush)
+    record("config4", ms, n4 * world, T4, ifv4, "strong", f"{len(names)} data/trajs trajectories x {seeds_total} noise seeds, "
+           f"30 Hz camera / {ifv4} IMU samples per frame, {frames} frames ({T4} propagates + {E4} updates per filter), streams "
+           f"from the device pre-pass; seeds sharded over {world} GPU(s)", summarise_stats(sm.cpu().numpy()), 3)
+    del w, ds
+
+    # ---- config 5: 1,048,576 Monte-Carlo filters, sharded; NCCL all-reduce of the calibration statistics inside ----
+    n5 = 1 << 20
+    first, cnt = shard_of(n5, rank, world)
+    gen = torch.Generator(device=dev).manual_seed(7 + rank)
+    x5 = t64(sc.x0).repeat(cnt, 1)
+    x5[:, 10:13] += torch.randn((cnt, 3), generator=gen, dtype=torch.float64, device=dev) * np.deg2rad(3.0)
+    x5[:, 13:16] += torch.randn((cnt, 3), generator=gen, dtype=torch.float64, device=dev) * 3.0
+    with BatchFilter(cnt, device=local, **wl.model) as bf:
+        bf.set_noise(wl.Qd[None], wl.Rd[None], wl.sig_om[None])
+
+        def run5():
+            st, sm = bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], cam_ref=d["cam_ref"], imu_ref=d["imu_ref"],
+                            stats_on_device=True, seed=SEED, filter_id0=first, imu_noise_std=wl.imu_std,
+                            cam_noise_std=wl.cam_std)
+            allreduce_stats(sm)
+            return sm
+
+        ms, sm = _timed(run5, lambda: bf.set_state(x5, P0, u0, None), 2, barrier, flush)
+    record("config5", ms, n5, T, IFV, "strong", f"{n5} Monte-Carlo filters (Philox noise seeds, DOF IC perturbation) on "
+           f"mandala0_mono {N_FRAMES} frames x {IFV}, {cnt} filters per GPU on {world} GPU(s), all-reduce of the calibration "
+           "statistics inside", summarise_stats(sm.cpu().numpy()), 2)
+    del x5
+    torch.cuda.empty_cache()
+
+    # ---- calibration: config 2 with all six DOFs ESTIMATED (config.yaml freezes them; HEAD zeroes frozen DOFs, quirk Q7) ----
+    nc = a.filters
+    model = dict(wl.model, frozen_dofs=(0,) * 6)
+    xc = t64(mc_initial_states(sc.x0, nc, rank * nc))
+    with BatchFilter(nc, device=local, **model) as bf:
+        bf.set_noise(wl.Qd[None], wl.Rd[None], wl.sig_om[None])
+
+        def runc():
+            st, sm = bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], cam_ref=d["cam_ref"], imu_ref=d["imu_ref"],
+                            stats_on_device=True, seed=SEED, filter_id0=rank * nc, imu_noise_std=wl.imu_std,
+                            cam_noise_std=wl.cam_std, gt_dofs=tuple(wl.cfg.gt_imu_dofs))
+            allreduce_stats(sm)
+            return sm
+
+        ms, sm = _timed(runc, lambda: bf.set_state(xc, P0, u0, None), 5, barrier, flush)
+    record("calibration", ms, nc * world, T, IFV, "weak", f"config 2 with all six calibration DOFs estimated (none frozen): {nc} "
+           f"filters per GPU, per-filter DOF initial-condition perturbation N(0, 3 deg) / N(0, 3 cm), Philox noise; dof_rmse is the "
+           "calibration RMSE against the ground-truth DOFs", summarise_stats(sm.cpu().numpy()), 5)
+    return out
+
+
 def run_ours(a):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -346,34 +507,65 @@ def run_ours(a):
     h2d = sum(hp[k].nbytes for k in ("dt", "oa", "npr", "cam", "notch", "cam_ref", "imu_ref", "x0", "P0", "u0"))
     d2h = n * 16 * 8 + 16 * 8
 
-    def e2e_pass():
+    st_pin = torch.empty((n, 16), dtype=torch.float64).pin_memory()
+    sm_pin = torch.empty((16,), dtype=torch.float64).pin_memory()
+    x_pin = torch.empty((n, 26), dtype=torch.float64).pin_memory()
+    P_pin = torch.empty((n, 24, 24), dtype=torch.float64).pin_memory()
+
+    def e2e_pass(full_readback=False):
         bf.set_state(hp["x0"], hp["P0"], hp["u0"], None)
-        st_h, sm_h = bf.run(hp["dt"], hp["oa"], hp["npr"], hp["cam"], hp["notch"], cam_ref=hp["cam_ref"],
-                            imu_ref=hp["imu_ref"], **run_kw)
-        if dist is not None:
-            t = torch.from_numpy(sm_h).to(dev)
-            dist.all_reduce(t)
-            sm_h = t.cpu().numpy()
+        if dist is None:
+            st_h, sm_h = bf.run(hp["dt"], hp["oa"], hp["npr"], hp["cam"], hp["notch"], cam_ref=hp["cam_ref"],
+                                imu_ref=hp["imu_ref"], **run_kw)
+        else:
+            # host streams in, statistics left on the device: the reduced vector is all-reduced where it is and crosses
+            # the bus once (round 1 copied it down, up and down again)
+            st_d, sm_d = bf.run(hp["dt"], hp["oa"], hp["npr"], hp["cam"], hp["notch"], cam_ref=hp["cam_ref"],
+                                imu_ref=hp["imu_ref"], stats_on_device=True, **run_kw)
+            dist.all_reduce(sm_d)
+            st_pin.copy_(st_d, non_blocking=True)
+            sm_pin.copy_(sm_d, non_blocking=True)
+            torch.cuda.synchronize()
+            st_h, sm_h = st_pin.numpy(), sm_pin.numpy()
+        if full_readback:  # a caller that wants Filter._states / Filter._P of every filter, not only the error statistics
+            xd, Pd, _, _, _ = bf.get_state(device=True)
+            x_pin.copy_(xd, non_blocking=True)
+            P_pin.copy_(Pd, non_blocking=True)
+            torch.cuda.synchronize()
         return st_h, sm_h
 
-    for _ in range(2):
-        e2e_pass()
-    barrier()
-    e2e_ms = []
-    for _ in range(a.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        st_h, sm_h = e2e_pass()  # returns after the D2H read of the statistics
-        e2e_ms.append(1e3 * (time.perf_counter() - t0))
-    barrier()
-    e2e_t = float(np.mean(e2e_ms))
+    def e2e_time(full_readback):
+        for _ in range(2):
+            e2e_pass(full_readback)
+        barrier()
+        ts = []
+        for _ in range(a.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e2e_pass(full_readback)  # returns after the D2H read of the statistics (and of x, P with full_readback)
+            ts.append(1e3 * (time.perf_counter() - t0))
+        barrier()
+        return float(np.mean(ts))
+
+    e2e_t = e2e_time(False)
+    e2e_full_t = e2e_time(True)
+    d2h_full = d2h + n * (26 + 576) * 8
+
+    # ---- BASELINE configs 3 / 4 / 5 and the calibration variant, same run, same clock sampler ----
+    secondary = None
+    if not a.no_configs:
+        sampler2 = ClockSampler(local)
+        if rank == 0:
+            sampler2.start()
+        secondary = secondary_workloads(a, wl, dev, local, rank, world, dist, flush, barrier)
+        clocks2 = sampler2.stop() if rank == 0 else None
 
     # max over ranks
     if dist is not None:
-        tt = torch.tensor([ms, e2e_t], dtype=torch.float64, device=dev)
+        tt = torch.tensor([ms, e2e_t, e2e_full_t], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, e2e_t = float(tt[0]), float(tt[1])
+        ms, e2e_t, e2e_full_t = float(tt[0]), float(tt[1]), float(tt[2])
     total_steps = float(n) * T * world
     value = total_steps / (ms * 1e-3)
     e2e_val = total_steps / (e2e_t * 1e-3)
@@ -405,13 +597,24 @@ def run_ours(a):
             "config": workload_config(n, T, E, world, a.fpc),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_t},
+                    "ms_per_step": e2e_t,
+                    "result": "per-filter error statistics [N,16] + the reduced vector (the result of a Monte-Carlo job: "
+                              "calibration RMSE, update MSE); the final x, P stay on the device -- see e2e_full_readback"},
+            "e2e_full_readback": {"value": total_steps / (e2e_full_t * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                                  "d2h_bytes_per_step": int(d2h_full), "ms_per_step": e2e_full_t,
+                                  "result": "statistics + final state x [N,26] and covariance P [N,24,24] of every filter"},
             "gpu_launches": int(launches_timed),
             "roofline": roofline,
             "cpu_baseline": cpu,
             "wall_s_timed_loop": t_wall,
             "stats": summarise_stats(stats_sum),
         }
+        if secondary is not None:
+            for v in secondary.values():
+                v["achieved_tflops"] = v["value"] * v["flops_per_filter_step"] * 1e-12
+                v["frac"] = v["achieved_tflops"] / peak_tf
+            line["configs"] = secondary
+            line["configs_clocks"] = clocks2
         print(json.dumps(line), flush=True)
     bf.close()
     if dist is not None:
@@ -429,6 +632,7 @@ def main():
     ap.add_argument("--fpc", type=int, default=0, help="filters per CTA (0 = automatic)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the secondary workloads (BASELINE configs 3 / 4 / 5, calibration)")
     a = ap.parse_args()
     if a.impl == "reference":
         return run_reference_arm(a)

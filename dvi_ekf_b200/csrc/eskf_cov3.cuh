@@ -20,6 +20,15 @@
 #ifndef ESKF_OPT_UPD
 #define ESKF_OPT_UPD 1  // hand-pipelined record fetches in the loops of the camera update
 #endif
+#ifndef ESKF_OPT_FIN14
+#define ESKF_OPT_FIN14 0  // Joseph form: both sums of upd3_finish as one rolled loop of fourteen columns
+#endif
+#ifndef ESKF_OPT_QP
+#define ESKF_OPT_QP 0  // process-noise diagonal as predicated adds
+#endif
+#ifndef ESKF_OPT_ST1
+#define ESKF_OPT_ST1 1  // pass 1: the stores of the identity rows are spread over the multiply-adds of the other row groups
+#endif
 
 namespace eskf {
 
@@ -169,6 +178,98 @@ ESKF_HD void fx3_apply_store(const double (&X)[24][3], const d2* f2, double* out
     out[15 * OS + v] = X[15][v] + dt * X[16][v];
     out[16 * OS + v] = X[16][v] + dt * X[17][v];
   }
+}
+
+// Pass 1 with the 72 stores spread over the 222 multiply-adds (ESKF_OPT_ST1): as written above the identity rows leave as
+// one burst of 21 stores at the head of the pass, in all covariance warps of the CTA at the same time, and the shared-memory
+// queue throttles (ncu: ~8 cycles per store there against ~2 for the stores that sit between multiply-adds).  Same
+// operations per accumulator in the same order: bit-identical.
+template <int PS, int OS>
+ESKF_HD void fx3_apply_store_il(const double (&X)[24][3], const d2* f2, double* out) {
+  const double dt = f2[(FX3_DT / 2) * PS].x;
+  auto putX = [&](int row) {
+#pragma unroll
+    for (int v = 0; v < 3; ++v) out[row * OS + v] = X[row][v];
+  };
+  double y[3][3], z[3][3], w[3][3];
+  // rows 21:24; between its seven columns: identity rows 9..14 and 17
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) y[i][v] = (i == 0) ? 0.0 : X[21 + i][v];
+#pragma unroll
+  for (int kb = 0; kb < 7; kb += 2) {
+    Coefs<PS, 6> c;
+    c.load(f2, FX3_H2 + 3 * kb);
+#pragma unroll
+    for (int k = kb; k < kb + 2 && k < 7; ++k) {
+      const int col = (k < 3) ? 9 + k : (k == 3) ? 15 : 19 + (k - 4);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int v = 0; v < 3; ++v) y[i][v] += c(3 * (k - kb) + i) * X[col][v];
+      putX(k < 6 ? 9 + k : 17);
+    }
+  }
+  // rows 18:21; between its nine columns: the finished rows 21:24, rows 0:3 (p += dt v) and the notch chain
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) z[i][v] = X[16 + i][v] + dt * X[3 + i][v];
+#pragma unroll
+  for (int kb = 0; kb < 9; kb += 2) {
+    Coefs<PS, 6> c;
+    c.load(f2, FX3_H1 + 3 * kb);
+#pragma unroll
+    for (int k = kb; k < kb + 2 && k < 9; ++k) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int v = 0; v < 3; ++v) z[i][v] += c(3 * (k - kb) + i) * X[6 + k][v];
+      if (k < 3) {
+#pragma unroll
+        for (int v = 0; v < 3; ++v) out[(21 + k) * OS + v] = y[k][v];
+      } else if (k < 6) {
+#pragma unroll
+        for (int v = 0; v < 3; ++v) out[(k - 3) * OS + v] = X[k - 3][v] + dt * X[k][v];
+      } else if (k == 6) {
+#pragma unroll
+        for (int v = 0; v < 3; ++v) out[15 * OS + v] = X[15][v] + dt * X[16][v];
+      } else if (k == 7) {
+#pragma unroll
+        for (int v = 0; v < 3; ++v) out[16 * OS + v] = X[16][v] + dt * X[17][v];
+      }
+    }
+  }
+  // rows 3:9; between its three columns: the finished rows 18:21
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      y[i][v] = X[3 + i][v];
+      w[i][v] = 0.0;
+    }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    Coefs<PS, 6> c;
+    c.load(f2, FX3_AB + 6 * k);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        y[i][v] += c(i) * X[6 + k][v];
+        w[i][v] += c(3 + i) * X[6 + k][v];
+      }
+#pragma unroll
+    for (int v = 0; v < 3; ++v) out[(18 + k) * OS + v] = z[k][v];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      out[(3 + i) * OS + v] = y[i][v];
+      out[(6 + i) * OS + v] = w[i][v];
+    }
 }
 
 // Pass 2: X <- Fx X in place.
@@ -358,12 +459,24 @@ ESKF_HD void fx3_noise_diag(int g, const QD& qd, double (&qdv)[3]) {
 // Fi Q Fi^T for the tile of lane group g (Filter.py:349).
 template <int PS, typename QD>
 ESKF_HD void fx3_process_noise(double (&X)[24][3], int g, const d2* f2, const double (&qdv)[3], const QD& qd, bool imu_q) {
-  // diagonal entries P'(3g+v, 3g+v) = X[3g+v][v]: branch-free selects, every index is a constant
+  // diagonal entries P'(3g+v, 3g+v) = X[3g+v][v]: every index is a constant
+#if ESKF_OPT_QP
+  // (predicated adds: four predicates instead of two selects per addend)
+#pragma unroll
+  for (int j = 1; j < 5; ++j) {
+    if (g == j) {
+#pragma unroll
+      for (int v = 0; v < 3; ++v) X[3 * j + v][v] += qdv[v];
+    }
+  }
+  if (g == 5) X[17][2] += qdv[2];
+#else
 #pragma unroll
   for (int j = 1; j < 5; ++j)
 #pragma unroll
     for (int v = 0; v < 3; ++v) X[3 * j + v][v] += (g == j) ? qdv[v] : 0.0;
   X[17][2] += (g == 5) ? qdv[2] : 0.0;
+#endif
   if (imu_q && (g == 2 || g == 6 || g == 7)) {
     // n_om drives theta (I), p_C (Np) and theta_C (Nt): L Q_om L^T on rows/cols {6:9,18:21,21:24};
     // the diagonal of the theta block was added above.
@@ -635,7 +748,49 @@ ESKF_HD void upd3_finish(double (&X)[24][3], int g, const double* rec, const dou
   for (int i = 0; i < 24; ++i)
 #pragma unroll
     for (int v = 0; v < 3; ++v) X[i][v] = cdv[v] * X[i][v];
-#if ESKF_OPT_UPD
+#if ESKF_OPT_UPD && ESKF_OPT_FIN14
+  {  // both sums as ONE rolled loop of fourteen columns (t < 7: - W(:,h_t) K[j][t] with the measured column masked;
+     // t >= 7: + K(:,m) R_m K[j][m]): one loop body in the instruction cache and no drain / refill of the hand-made
+     // pipeline between the two sweeps.  fma(w, -z, x) is the same rounding as x - w z: bit-identical to the two sweeps.
+    double kv[3], rdm = 0.0, ba[4], bb[4], bc[4];
+    auto pre = [&](int t) {
+      const int m = t < 7 ? t : t - 7;
+      const int base = t < 7 ? U3_WH : U3_K;
+#pragma unroll
+      for (int v = 0; v < 3; ++v) kv[v] = u3_get<QS>(rec, U3_K + 24 * m + 3 * g + v);
+      rdm = rd[m * RDS];
+      u3_get4<QS>(rec, base + 24 * m + 0, ba);
+      u3_get4<QS>(rec, base + 24 * m + 4, bb);
+    };
+    auto blk = [&](int ib, const double (&w)[4], const double (&z)[3]) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int v = 0; v < 3; ++v) X[ib + r][v] += w[r] * z[v];
+    };
+    pre(0);
+#pragma unroll 1
+    for (int t = 0; t < 14; ++t) {
+      const int m = t < 7 ? t : t - 7;
+      const int base = t < 7 ? U3_WH : U3_K;
+      double z[3];
+#pragma unroll
+      for (int v = 0; v < 3; ++v) z[v] = (t < 7) ? ((u3_hset(m) == 3 * g + v) ? -0.0 : -kv[v]) : rdm * kv[v];
+      u3_get4<QS>(rec, base + 24 * m + 8, bc);
+      blk(0, ba, z);
+      u3_get4<QS>(rec, base + 24 * m + 12, ba);
+      blk(4, bb, z);
+      u3_get4<QS>(rec, base + 24 * m + 16, bb);
+      blk(8, bc, z);
+      u3_get4<QS>(rec, base + 24 * m + 20, bc);
+      blk(12, ba, z);
+      const double b16[4] = {bb[0], bb[1], bb[2], bb[3]}, b20[4] = {bc[0], bc[1], bc[2], bc[3]};
+      pre(t < 13 ? t + 1 : 13);
+      blk(16, b16, z);
+      blk(20, b20, z);
+    }
+  }
+#elif ESKF_OPT_UPD
   {  // software pipelined by hand (see upd3_w_pass): fetches two blocks ahead, the next column's first blocks at the end
     double kv[3], rdm, ba[4], bb[4], bc[4];
     auto blk = [&](int ib, const double (&w)[4], const double (&z)[3], bool sub) {

@@ -68,6 +68,9 @@
 #ifndef ESKF_OPT_TMA
 #define ESKF_OPT_TMA 0  // sample stream staged by cp.async.bulk chunks (see CH3_STEPS)
 #endif
+#ifndef ESKF_OPT_ADDR
+#define ESKF_OPT_ADDR 0  // covariance role: buffer offsets kept in (laundered) registers instead of being re-derived every step
+#endif
 #ifndef ESKF_OPT_STREAM
 #define ESKF_OPT_STREAM 1  // pass 2 streams the transposed tile from the buffer (reload fused into the pass)
 #endif
@@ -137,8 +140,11 @@ struct Lay3 {
   static constexpr int MBAR = FXB + 2 * FX3_NPAIR * 2 * F;   // 4 mbarriers: full[2], empty[2]
 #if ESKF_OPT_TMA
   static constexpr int CHBAR = MBAR + 4;                     // 2 mbarriers: chunk[2] of the staged sample stream
-  static constexpr int CHUNK = CHBAR + 2;                    // [2][CH3_STEPS * 7]: om_acc (6 per step) then dt (1 per step)
-  static constexpr int TOTAL = CHUNK + 2 * CH3_STEPS * 7;    // doubles
+  // [2][CHW]: a chunk of the shared stream (om_acc, 6 per step, then dt, 1 per step) or, in pre-pass mode, the block of one
+  // step of the per-filter stream (6 per filter)
+  static constexpr int CHW = (CH3_STEPS * 7 > F * 6) ? CH3_STEPS * 7 : F * 6;
+  static constexpr int CHUNK = CHBAR + 2;
+  static constexpr int TOTAL = CHUNK + 2 * CHW;              // doubles
   static_assert((CHUNK % 2) == 0, "16-byte alignment of the bulk-copy destination");
 #else
   static constexpr int TOTAL = MBAR + 4;                     // doubles
@@ -329,7 +335,7 @@ __device__ __forceinline__ void trace_dofs(double* r, const double* dofs, const 
 
 // ---------------------------------------------------------------------------------------------
 // role 0: IMU nominal state
-template <int F, int NTHR>
+template <int F, int NTHR, bool EX>
 __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lane) {
   using L = Lay3<F>;
   const bool act = lane < c.nf;
@@ -392,7 +398,7 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
 #pragma unroll
           for (int j = FX3_AB / 2; j < FX3_MAIN / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
 #if ESKF_OPT_JACDUMP
-          if (a.fx_dump && kk == a.T - 1) {  // Filter.Fx / Filter.Fi read-out: the record of the last step of the launch
+          if (EX && a.fx_dump && kk == a.T - 1) {  // Filter.Fx / Filter.Fi read-out: the record of the last step of the launch
             double* fd = a.fx_dump + (c.f0 + lane) * FX3_SIZE;
 #pragma unroll
             for (int j = FX3_AB; j < FX3_MAIN; ++j) fd[j] = fx[j];
@@ -401,7 +407,7 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
         }
 #endif
         imu_nominal_step(p, v, q, Rwb, dt, om_old, acc_old, om, acc, Rold);
-        if (a.trace) trace_pvq(a.trace + ((c.f0 + lane) * a.T + kk) * NX, p, v, q);
+        if (EX && a.trace) trace_pvq(a.trace + ((c.f0 + lane) * a.T + kk) * NX, p, v, q);
         const int s = (int)((kk + 1) & 1);
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
@@ -451,7 +457,7 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
 #pragma unroll
         for (int i = 0; i < 4; ++i) q[i] = qn[i];
         quat_to_rot(q, Rwb);  // R_WB of the next step; R_WB_old keeps the pre-update value (quirk Q8)
-        if (a.trace && k > 0) trace_pvq(a.trace + ((c.f0 + lane) * a.T + k - 1) * NX, p, v, q);  // FilterTraj.append_updated_states
+        if (EX && a.trace && k > 0) trace_pvq(a.trace + ((c.f0 + lane) * a.T + k - 1) * NX, p, v, q);  // FilterTraj.append_updated_states
         const int s = (int)(k & 1);
 #pragma unroll
         for (int i = 0; i < 9; ++i) sx[(SX3_RW + 9 * s + i) * F] = Rwb[i];
@@ -504,7 +510,7 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
 
 // ---------------------------------------------------------------------------------------------
 // role 1: camera nominal state + measurement residual
-template <int F, int NTHR>
+template <int F, int NTHR, bool EX>
 __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lane) {
   using L = Lay3<F>;
   const bool act = lane < c.nf;
@@ -558,7 +564,7 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
         const double dt = un[6 * F];
         const double notch_d = sx[(SX3_PK + PK3 * s + 16) * F];
         cam_nominal_step(pc, qc, vpre, Rwb, dt, om_old, om, pkp, pkR, pkz, notch_d);
-        if (a.trace) trace_cam(a.trace + ((c.f0 + lane) * a.T + kk) * NX, pc, qc);
+        if (EX && a.trace) trace_cam(a.trace + ((c.f0 + lane) * a.T + kk) * NX, pc, qc);
       }
       PT_MARK(1);
       pk_ready_wait();
@@ -596,7 +602,7 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
 #pragma unroll
         for (int j = FX3_H1 / 2; j < FX3_AB / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
 #if ESKF_OPT_JACDUMP
-        if (a.fx_dump && kk == a.T - 1) {
+        if (EX && a.fx_dump && kk == a.T - 1) {
           double* fd = a.fx_dump + (c.f0 + lane) * FX3_SIZE;
 #pragma unroll
           for (int j = FX3_H1; j < FX3_AB; ++j) fd[j] = fx[j];
@@ -652,7 +658,7 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
 #pragma unroll
         for (int i = 0; i < 4; ++i) qc[i] = qn[i];
         n_upd += 1.0;
-        if (a.trace && k > 0) trace_cam(a.trace + ((c.f0 + lane) * a.T + k - 1) * NX, pc, qc);
+        if (EX && a.trace && k > 0) trace_cam(a.trace + ((c.f0 + lane) * a.T + k - 1) * NX, pc, qc);
       } else {
         st |= ESKF_STATUS_UPDATE_SKIPPED;
       }
@@ -695,7 +701,7 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
 // role 2: dofs / notch, probe kinematics, Jacobian blocks (rows 21:24 and the noise rows; rows 3:9 come from the IMU
 // role, rows 18:21 from the CAMERA role).
 // The probe kinematics and their trigonometry cache live in shared memory (PK slots, TR), not in registers.
-template <int F, int NTHR>
+template <int F, int NTHR, bool EX>
 __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lane) {
   using L = Lay3<F>;
   const bool act = lane < c.nf;
@@ -752,7 +758,7 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
           for (int i = 0; i < PK_SIZE; ++i) pk.b[i * F] = po.b[i * F];
         }
         put_notch(sn, notch, dofs);
-        if (a.trace) trace_dofs(a.trace + ((c.f0 + lane) * a.T + kk) * NX, dofs, notch);
+        if (EX && a.trace) trace_dofs(a.trace + ((c.f0 + lane) * a.T + kk) * NX, dofs, notch);
       }
       pk_ready_arrive();  // the CAMERA warp takes rows 18:21 from here
 #if ESKF_OPT_LATEACQ
@@ -808,7 +814,7 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
           for (int j = FX3_NPAIR_MAIN; j < FX3_NPAIR; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
         }
 #if ESKF_OPT_JACDUMP
-        if (a.fx_dump && kk == a.T - 1) {  // (rows 18:24 of Fi are part of the read-out whether or not Q uses them)
+        if (EX && a.fx_dump && kk == a.T - 1) {  // (rows 18:24 of Fi are part of the read-out whether or not Q uses them)
           double* fd = a.fx_dump + (c.f0 + lane) * FX3_SIZE;
           if (!imu_q) {
             double Ro[9];
@@ -846,7 +852,7 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
         for (int i = 0; i < 3; ++i) notch[i] += sx[(SX3_DELTA + 15 + i) * F];
         probe_update_v(a.model, dofs, notch, pkv((int)(k & 1)), trv);
         put_notch((int)(k & 1), notch, dofs);
-        if (a.trace && k > 0) trace_dofs(a.trace + ((c.f0 + lane) * a.T + k - 1) * NX, dofs, notch);
+        if (EX && a.trace && k > 0) trace_dofs(a.trace + ((c.f0 + lane) * a.T + k - 1) * NX, dofs, notch);
       }
     }
     PT_MARK(6);
@@ -888,25 +894,37 @@ __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int l
   const bool noisy = a.noise_on && !(a.noise_free0 && gid == 0);
   const double* oap =
       a.om_acc ? (a.stream_per_filter ? a.om_acc + (c.f0 + lane) * a.T * 6 : a.om_acc + c.traj * a.T * 6) : nullptr;
+  const int64_t oas = 6;
 #endif
 #if ESKF_OPT_TMA
-  // chunk c = samples [c CH3_STEPS, (c + 1) CH3_STEPS) -> buffer c & 1; complete chunks only (the tail goes the plain way);
-  // needs the shared stream (one trajectory per CTA) and 16-byte aligned chunk sources
+  // Bulk-asynchronous staging (TMA unit, cp.async.bulk completed on an mbarrier), two buffers in flight; lane 0 issues.
+  //  * shared stream (one trajectory per CTA, no pre-pass): chunk ch = samples [ch CH3_STEPS, (ch + 1) CH3_STEPS) of om_acc
+  //    and dt -> buffer ch & 1; complete chunks only (the tail goes the plain way); needs 16-byte aligned chunk sources.
+  //  * pre-pass mode (imu_pf [T][N][6]): the samples of the CTA's filters for ONE step are contiguous (nf x 48 bytes):
+  //    one copy per step -> buffer j & 1, issued one step ahead.
+  // A buffer is re-filled only after every lane of this warp has passed the scalar barrier that follows its last read.
   uint64_t* chbar = reinterpret_cast<uint64_t*>(c.smem + L::CHBAR);
   double* chunk = c.smem + L::CHUNK;
   const double* oa0 = a.om_acc ? a.om_acc + c.traj * a.T * 6 : nullptr;
-  const bool tma = oa0 && c.dtp && !a.stream_per_filter && ((reinterpret_cast<uintptr_t>(oa0) & 15) == 0) &&
+  const bool tma_pf = a.imu_pf != nullptr && c.nf > 0;
+  const bool tma = !tma_pf && oa0 && c.dtp && !a.stream_per_filter && ((reinterpret_cast<uintptr_t>(oa0) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(c.dtp) & 15) == 0);
   const int64_t n_chunks = tma ? a.T / CH3_STEPS : 0;
-  // (lane 0 issues.  The buffer held chunk ch - 2, last read before the scalar barrier of the previous step: every lane
-  // of this warp has passed that barrier, so nobody still reads it)
   auto issue_chunk = [&](int64_t ch) {
     if (lane == 0 && ch < n_chunks) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      double* buf = chunk + (int)(ch & 1) * CH3_STEPS * 7;
+      double* buf = chunk + (int)(ch & 1) * L::CHW;
       mbar_expect_tx(chbar + (ch & 1), CH3_STEPS * 56);
       bulk_g2s(buf, oa0 + ch * CH3_STEPS * 6, CH3_STEPS * 48, chbar + (ch & 1));
       bulk_g2s(buf + CH3_STEPS * 6, c.dtp + ch * CH3_STEPS, CH3_STEPS * 8, chbar + (ch & 1));
+    }
+  };
+  auto issue_step = [&](int64_t j) {
+    if (lane == 0 && tma_pf && j < a.T) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const uint32_t bytes = (uint32_t)c.nf * 48u;
+      mbar_expect_tx(chbar + (j & 1), bytes);
+      bulk_g2s(chunk + (int)(j & 1) * L::CHW, a.imu_pf + (j * a.N + c.f0) * 6, bytes, chbar + (j & 1));
     }
   };
 #endif
@@ -916,17 +934,24 @@ __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int l
 #if ESKF_OPT_TMA
     double dtj;
     const int64_t ch = j / CH3_STEPS;
-    if (ch < n_chunks) {
+    if (tma_pf) {
+      issue_step(j + 1);  // its buffer held step j - 1: every lane is done with it
+      mbar_wait(chbar + (j & 1), (uint32_t)((j >> 1) & 1));
+      const double* buf = chunk + (int)(j & 1) * L::CHW + lane * 6;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) u[i] = buf[i];
+      dtj = c.dtp[j];
+    } else if (ch < n_chunks) {
       const int jj = (int)(j - ch * CH3_STEPS);
       if (jj == 0) issue_chunk(ch + 1);  // its buffer held chunk ch - 1: every lane is done with it
       mbar_wait(chbar + (ch & 1), (uint32_t)((ch >> 1) & 1));
-      const double* buf = chunk + (int)(ch & 1) * CH3_STEPS * 7;
+      const double* buf = chunk + (int)(ch & 1) * L::CHW;
 #pragma unroll
       for (int i = 0; i < 6; ++i) u[i] = buf[jj * 6 + i];
       dtj = buf[CH3_STEPS * 6 + jj];
     } else {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) u[i] = oap[j * 6 + i];
+      for (int i = 0; i < 6; ++i) u[i] = oap[j * oas + i];
       dtj = c.dtp[j];
     }
 #elif ESKF_OPT_PP
@@ -1030,6 +1055,7 @@ __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int l
   }
 #if ESKF_OPT_TMA
   issue_chunk(0);
+  issue_step(0);
 #endif
   if (act && a.T > 0 && oap) stage_sample(0);
   __syncthreads();  // prologue
@@ -1242,6 +1268,10 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
   // of IMU samples per frame).  The covariance is symmetric only up to the reference's own rounding, which an
   // ill-conditioned tuning makes large enough to matter.
   load_rows();
+#if ESKF_OPT_ADDR
+  int o_fx = cf, o_tbw = cf * TB3_STRIDE + 3 * cg, o_tbr = cf * TB3_STRIDE + 3 * cg * RS3;
+  asm volatile("" : "+r"(o_fx), "+r"(o_tbw), "+r"(o_tbr));  // (opaque: not re-derived from the thread index inside the loop)
+#endif
   __syncthreads();  // prologue
   PT_DECL();
 #ifdef ESKF_EXP_STAGGER  // (profiling experiment: the second covariance warp of every sub-partition starts late)
@@ -1263,10 +1293,22 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
       const int64_t kk = k + it;
       const bool step = it < n;
       if (ESKF3_COV_ON) {
+#if ESKF_OPT_ADDR
+        const d2* f2 = reinterpret_cast<const d2*>(c.smem + L::FXB) + o_fx + ((int)(kk & 1) * FX3_NPAIR) * F;
+        double* const TBW = c.smem + L::TB + o_tbw;
+        const double* const TBR = c.smem + L::TB + o_tbr;
+#else
         const d2* f2 = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
+        double* const TBW = Tb + 3 * cg;
+        const double* const TBR = Tb + 3 * cg * RS3;
+#endif
         if (step) {
           // pass 1: T(:, 3g..3g+2) = Fx P(:, 3g..3g+2), rows stored as they are finished
-          fx3_apply_store<F, RS3>(X, f2, Tb + 3 * cg);
+#if ESKF_OPT_ST1
+          fx3_apply_store_il<F, RS3>(X, f2, TBW);
+#else
+          fx3_apply_store<F, RS3>(X, f2, TBW);
+#endif
         } else {
 #pragma unroll
           for (int i = 0; i < 24; ++i)
@@ -1282,7 +1324,7 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
           break;
         }
         // pass 2 fused with the transposed reload: P'(3g+v, :) = Fx T(3g+v, :)^T, T streamed from the buffer
-        fx3_apply_stream<F, RS3>(X, f2, Tb + 3 * cg * RS3);
+        fx3_apply_stream<F, RS3>(X, f2, TBR);
         PT_MARK(4);
         // the record of the NEXT step: its producers stored it one step ago (ESKF_OPT_LATEACQ) -- normally no wait
         if (it + 1 < n) fx_slot_wait(c.mbar, kk + 1);
@@ -1371,7 +1413,7 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int F, int REG_S, int REG_C>
+template <int F, int REG_S, int REG_C, bool EX>
 __global__ void __launch_bounds__(128 + 8 * F, 1) eskf_kernel3(const __grid_constant__ KArgs a) {
   extern __shared__ __align__(16) double smem[];
   using L = Lay3<F>;
@@ -1422,13 +1464,13 @@ __global__ void __launch_bounds__(128 + 8 * F, 1) eskf_kernel3(const __grid_cons
     // share REG_S although the Jacobian warp's sub-partition would have room for more)
     reg_dec3<REG_S>();
     if (warp == 0)
-      role3_imu<F, NTHR>(a, c, lane);
+      role3_imu<F, NTHR, EX>(a, c, lane);
     else if (warp == 1)
-      role3_cam<F, NTHR>(a, c, lane);
+      role3_cam<F, NTHR, EX>(a, c, lane);
     else if (warp == 2)
       role3_stage<F, NTHR>(a, c, lane);
     else
-      role3_jac<F, NTHR>(a, c, lane);
+      role3_jac<F, NTHR, EX>(a, c, lane);
   }
 }
 

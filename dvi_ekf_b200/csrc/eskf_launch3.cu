@@ -30,7 +30,9 @@ cudaError_t launch_eskf_kernel3<ESKF_F>(const KArgs& a, cudaStream_t stream) {
   static_assert(ESKF_REG_S == 0 || ESKF_REG_S + 2 * ESKF_REG_C <= 504, "register split exceeds a sub-partition");
   constexpr size_t smem = (size_t)Lay3<F>::TOTAL * sizeof(double);
   static_assert(smem <= 232448, "shared memory per CTA");
-  auto kern = eskf_kernel3<F, ESKF_REG_S, ESKF_REG_C>;
+  // export mode (FilterTraj rows, eskf_streams_t.trace_x; Jacobian record of the last step, eskf_keep_jacobians) is a second
+  // instantiation: the production kernel carries none of its code (the dump alone cost 10 % through register allocation)
+  auto kern = (a.trace || a.fx_dump) ? eskf_kernel3<F, ESKF_REG_S, ESKF_REG_C, true> : eskf_kernel3<F, ESKF_REG_S, ESKF_REG_C, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)((a.N + F - 1) / F);

@@ -160,6 +160,118 @@ def test_batched_tuner_population_in_one_launch():
     assert ret.fun <= sim.evaluate_candidates(np.array([ret.x]), runs_per_candidate=3)[0] + 1e-12
 
 
+def test_tuner_objective_matches_oracle(golden, tmp_path):
+    """SURVEY 8f rank 3, parity proper: ``Simulator.evaluate_candidates`` (the objective of Simulator.optimise,
+    Simulator.py:163-245; Filter.calculate_dof_metric Filter.py:452-455 and the update MSE Filter.py:397-418) for
+    2 candidates x 3 runs with all six DOFs estimated, against the ORACLE run filter by filter on the same inputs: the noise
+    the kernels drew is read back with eskf_noise_dump (ids 0..r-1: noise_id_modulus = r), the initial-condition perturbation
+    is rng([seed, i % r]) and every candidate has its own Q / R."""
+    import os
+
+    import yaml
+
+    from dvi_ekf_b200 import Config, Simulator
+    from dvi_ekf_b200.engine import NOISE_CAM, NOISE_IMU, noise_samples
+    from oracle.eskf_oracle import euler_xyz_deg, quat_about_axis, quat_mul
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    y = yaml.safe_load(open(os.path.join(root, "config.yaml")))
+    frames, ifv, r = 14, 5, 3
+    y["simulation"].update(do_fast_sim=False, frozen_dofs=[0] * 6)
+    y["camera"]["total_frames"] = frames
+    y["imu"]["interframe_vals"] = ifv
+    fp = tmp_path / "config.yaml"
+    fp.write_text(yaml.safe_dump(y))
+    cfg = Config(str(fp))
+    sim = Simulator(cfg)
+    b = cfg.batch
+    base = np.array([*cfg.process_noise_rw_std, *cfg.meas_noise_std], dtype=float)
+    X = np.array([base, base * np.linspace(0.5, 2.0, 14)])
+    f_dof = sim.evaluate_candidates(X, runs_per_candidate=r, metric="dof")
+    f_upd = sim.evaluate_candidates(X, runs_per_candidate=r, metric="update")
+
+    sc = mandala_scenario(golden, n_frames=frames, ifv=ifv, frozen_dofs=(0,) * 6)
+    s = sim.streams
+    T, E = len(sc.dt), len(sc.n_prop)
+    assert T == len(s.dt) and E == len(s.n_prop) and np.abs(sc.om_acc - s.om_acc).max() < 1e-9
+    imu_std = np.hstack((cfg.imu.stdev_omega, cfg.imu.stdev_accel))
+    cam_std = np.array(cfg.meas_noise_std)
+    zi = noise_samples(b.seed, 0, r, 0, T, NOISE_IMU)
+    zc = noise_samples(b.seed, 0, r, 0, E, NOISE_CAM)
+    gt = np.asarray(cfg.gt_imu_dofs, dtype=float)
+    ref_dof, ref_upd = np.zeros((2, r)), np.zeros((2, r))
+    for c in range(2):
+        for j in range(r):
+            x0 = sc.x0.copy()
+            oa, cam, notch = sc.om_acc.copy(), sc.cam_meas.copy(), sc.notch_meas.copy()
+            if j:  # run 0 of every candidate: nominal initial state, noise free
+                rng = np.random.default_rng([b.seed, j])
+                x0[10:13] += rng.normal(0.0, np.deg2rad(b.dof_ic_std_deg), 3)
+                x0[13:16] += rng.normal(0.0, b.dof_ic_std_cm, 3)
+                oa = oa + imu_std[None, :] * zi[j][:, :6]
+                for e in range(E):
+                    cam[e, :3] += cam_std[:3] * zc[j][e, :3]
+                    dth = cam_std[3:6] * zc[j][e, 3:6]
+                    nq = np.linalg.norm(cam[e, 3:])
+                    cam[e, 3:] = quat_mul(cam[e, 3:], quat_about_axis(np.linalg.norm(dth), dth)) * nq
+                    notch[e] += cam_std[6] * zc[j][e, 6]
+            kf = sc.new_oracle(x0=x0)
+            kf.Q = np.diag(np.hstack((np.zeros(6), np.square(X[c, 0:7]))))
+            kf.R = np.diag(np.square(X[c, 7:14]))
+            k, acc = 0, 0.0
+            for e in range(E):
+                for _ in range(sc.n_prop[e]):
+                    kf.propagate(sc.dt[k], oa[k, :3], oa[k, 3:])
+                    k += 1
+                assert kf.update(cam[e, :3], cam[e, 3:], notch[e]) is not None
+                x = kf.x
+                acc += (np.sum(np.square(s.cam_ref[e] - np.hstack((x.p_cam, euler_xyz_deg(x.q_cam)))))
+                        + np.sum(np.square(np.hstack((x.v, euler_xyz_deg(x.q))) - s.imu_ref[e]))) / 12
+            d = kf.x.dofs - gt
+            ref_dof[c, j] = d @ d / 6
+            ref_upd[c, j] = acc / E
+    rd, ru = ref_dof.mean(axis=1), ref_upd.mean(axis=1)
+    print(f"tuner objective vs oracle: dof {np.abs(f_dof / rd - 1).max():.2e}, update {np.abs(f_upd / ru - 1).max():.2e}")
+    assert np.abs(f_dof / rd - 1).max() < 1e-8 and np.abs(f_upd / ru - 1).max() < 1e-8
+    assert abs(rd[0] / rd[1] - 1) > 1e-3 and ref_dof[0, 1] != ref_dof[0, 0]  # candidates and runs really differ
+
+
+def test_main_py_flow_reproduces_the_reference_artefacts(golden, tmp_path, capsys):
+    """The reference's main.py (main.py:3-8: Config -> Simulator -> run_once) followed by Filter.save (Filter.py:457-465),
+    through the mirror classes with ``batch.legacy_golden: true`` (the presets of the commit that wrote the artefacts):
+    the two files it writes are data/trajs/kf_best_mandala0_mono.txt and imu_ref_mandala0_mono.txt, number for number at the
+    9 printed decimals."""
+    import os
+
+    import yaml
+
+    from dvi_ekf_b200 import Config, Simulator
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    y = yaml.safe_load(open(os.path.join(root, "config.yaml")))
+    y["batch"]["legacy_golden"] = True
+    y["simulation"]["traj_path"] = str(tmp_path)  # Filter.save writes next to the trajectories
+    fp = tmp_path / "config.yaml"
+    fp.write_text(yaml.safe_dump(y))
+    config = Config(str(fp))
+    sim = Simulator(config)
+    sim.run_once()
+    sim.kf.save()
+    out = capsys.readouterr().out
+    assert "MSE" in out and "Singular" not in out
+    ours = np.loadtxt(tmp_path / "kf_best_mandala0_mono.txt")
+    ref = golden["kf_best_mandala0_mono"]
+    assert ours.shape == ref.shape == (10, 30)
+    assert np.abs(ours - ref).max() <= 1.0e-9 + 1e-15, np.abs(ours - ref).max()  # both sides rounded to 9 decimals
+    ours_imu = np.loadtxt(tmp_path / "imu_ref_mandala0_mono.txt")
+    ref_imu = golden["imu_ref_mandala0_mono"]
+    assert ours_imu.shape == ref_imu.shape == (9, 14)
+    assert np.abs(ours_imu - ref_imu).max() <= 1.0e-9 + 1e-15, np.abs(ours_imu - ref_imu).max()
+    # the attributes main.py's consumers read afterwards
+    assert len(sim.kf.traj.rows) == 10 and len(sim.kf.imu.ref_rows) == 9
+    assert sim.kf.Fx.shape == (24, 24) and sim.kf.Fi.shape == (24, 13) and np.isfinite(sim.kf._P).all()
+
+
 @pytest.mark.parametrize("variant", [3, 1])
 def test_ragged_and_empty_epochs(golden, variant):
     """epochs with 0, 1, 2 and many IMU samples in one launch (the record pipeline, the mid-step waits and the barriers

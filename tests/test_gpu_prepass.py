@@ -83,3 +83,30 @@ def test_filter_on_device_resident_streams(golden):
     assert np.all(st == 0)
     # inputs agree to ~1e-12 (two implementations of the pre-pass); 190 free-running steps
     assert state_err(xg[0], xr) < 1e-7 and cov_err(Pg[0], Pr, sc.Rd) < 1e-7
+
+
+ROUND_FLOOR = 5.0e-10  # the artefacts are printed with 9 decimals (files.py:68-82)
+
+
+def test_gpu_prepass_reproduces_the_reference_imu_ref_file(golden):
+    """eskf_prepass pinned to the reference's own artefact: its imu_ref rows (Imu.eval_expr_single / ImuRefTraj,
+    Imu.py:141-226) for the default main.py run are data/trajs/imu_ref_mandala0_mono.txt (9 x 14), to the file's rounding."""
+    _, dev = _both(golden, "traj_mandala0_mono", 10, 1, euler_mode="zyx_legacy")
+    rows = dev.imu_ref_rows.cpu().numpy()[: dev.n_steps]
+    ref = golden["imu_ref_mandala0_mono"]
+    assert rows.shape == ref.shape == (9, 14)
+    assert np.abs(rows - ref).max() <= ROUND_FLOOR, np.abs(rows - ref).max()
+
+
+@pytest.mark.parametrize("kp, ifv, nfr", [("0.006", 10, 140), ("0.01", 50, 140), ("2.0", 50, 70), ("1.0", 5, 70)])
+def test_gpu_prepass_reproduces_the_legacy_imu_ref_files(golden, kp, ifv, nfr):
+    """The interpolation path at interframe_vals > 1 (Interpolator.py:25-88: np.linspace / np.interp / slerp, then f_imu
+    with the ground-truth probe) on the DEVICE against the four legacy imu_ref_*_upd_* artefacts -- the same column set as
+    tests/test_oracle_golden.py (their velocity columns come from an older velocity definition)."""
+    _, dev = _both(golden, "traj_mandala0_mono", nfr, ifv, euler_mode="zyx_legacy")
+    rows = dev.imu_ref_rows.cpu().numpy()[: dev.n_steps]
+    ref = golden[f"imu_ref_legacy_Kp{kp}"]
+    assert rows.shape == ref.shape
+    assert np.all(dev.n_prop.cpu().numpy() == ifv)
+    cols = [0, 1, 2, 3, 7, 8, 9, 10, 11, 12, 13]
+    assert np.abs(rows[:, cols] - ref[:, cols]).max() <= ROUND_FLOOR, np.abs(rows[:, cols] - ref[:, cols]).max()

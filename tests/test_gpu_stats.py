@@ -76,7 +76,7 @@ def test_reduced_vector_masks_diverged_and_flagged_filters(golden, budget):
     sc, s = _streams(golden)
     n = 40
     x0 = np.repeat(s.x0[None], n, 0)
-    x0[5, 0] = np.nan  # diverged from the start
+    x0[5, 3] = np.nan  # diverged from the start (the velocity enters Filter.calculate_update_mse; a NaN position alone never leaves x[0:3])
     P0 = np.repeat(sc.P0[None], n, 0)
     P0[9] = 0.0
     Qd, Rd = np.repeat(sc.Qd[None], n, 0), np.repeat(sc.Rd[None], n, 0)
