@@ -1,6 +1,7 @@
 // C ABI of the B200 batched VI-ESKF engine (see include/eskf.h) and its small utility kernels.
 // The persistent kernel itself lives in eskf_kernel.cuh and is instantiated per CTA shape in
 // eskf_launch.cu.
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost nothing unless a profiler is attached
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -325,6 +326,13 @@ __global__ void expand_jac_kernel(const double* __restrict__ rec, int64_t n, dou
 
 thread_local std::string g_err;
 
+// NVTX range for the lifetime of a scope (nsys / ncu --nvtx timelines: eskf_run and its pre- / post-pass, eskf_propagate,
+// eskf_update, eskf_prepass; the reference's only instrumentation is the disabled timer at Imu.py:256,271)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -605,6 +613,7 @@ int eskf_set_noise(eskf_t* h, const double* Qdiag, int64_t nq, const double* Rdi
 }
 
 int eskf_propagate(eskf_t* h, const double* dt, const double* om_acc, int64_t T, int per_filter, int mem) {
+  NvtxRange nvtx_("eskf_propagate");
   if (!h || !dt || !om_acc || T < 0) {
     g_err = "eskf_propagate: bad argument";
     return ESKF_EINVAL;
@@ -627,6 +636,7 @@ int eskf_propagate(eskf_t* h, const double* dt, const double* om_acc, int64_t T,
 }
 
 int eskf_update(eskf_t* h, const double* cam, const double* notch, int per_filter, double* K_out, int mem) {
+  NvtxRange nvtx_("eskf_update");
   if (!h || !cam || !notch) {
     g_err = "eskf_update: bad argument";
     return ESKF_EINVAL;
@@ -666,6 +676,7 @@ int eskf_update(eskf_t* h, const double* cam, const double* notch, int per_filte
 }
 
 int eskf_run(eskf_t* h, const eskf_streams_t* sp, double* stats_out, double* stats_sum, int mem) {
+  NvtxRange nvtx_("eskf_run");
   if (!h || !sp || !sp->dt || !sp->om_acc || !sp->n_prop || !sp->cam || !sp->notch || sp->n_traj < 1) {
     g_err = "eskf_run: bad argument";
     return ESKF_EINVAL;
@@ -796,6 +807,7 @@ int eskf_run(eskf_t* h, const eskf_streams_t* sp, double* stats_out, double* sta
         if ((rc = stage_reserve(h, 9, b_imu))) return rc;
         if ((rc = stage_reserve(h, 10, b_meas))) return rc;
         const int64_t n1 = h->N * T, n2 = h->N * E;
+        NvtxRange nvtx_pp("eskf_run: Monte-Carlo pre-pass");
         pp_imu_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, h->stream>>>((double*)h->stage[9], a.om_acc, pp);
         pp_meas_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, h->stream>>>((double*)h->stage[10], a.cam, a.notch, pp);
         CK(cudaGetLastError());
@@ -811,8 +823,12 @@ int eskf_run(eskf_t* h, const eskf_streams_t* sp, double* stats_out, double* sta
     }
   }
 #endif
-  if ((rc = launch(h, a, fpt, nt > 1))) return rc;
+  {
+    NvtxRange nvtx_k("eskf_run: persistent kernel");
+    if ((rc = launch(h, a, fpt, nt > 1))) return rc;
+  }
   if (pp_stats) {
+    NvtxRange nvtx_ps("eskf_run: statistics post-pass");
     const int64_t n2 = h->N * E;
     pp_stats1_kernel<<<(unsigned)((n2 + 127) / 128), 128, 0, h->stream>>>(a.snap, a.cam_ref, a.imu_ref, pp);
     pp_stats2_kernel<<<(unsigned)((h->N + 63) / 64), 64, 0, h->stream>>>(a.snap, dstats, nullptr, pp);
@@ -822,6 +838,7 @@ int eskf_run(eskf_t* h, const eskf_streams_t* sp, double* stats_out, double* sta
   if (dsum) {
     const int64_t nblk = (h->N + RED_ROWS - 1) / RED_ROWS;
     if ((rc = stage_reserve(h, 12, (size_t)nblk * ESKF_NSTAT * sizeof(double)))) return rc;
+    NvtxRange nvtx_red("eskf_run: statistics reduction");
     stats_partial_kernel<<<(unsigned)nblk, 256, 0, h->stream>>>(dstats, h->status, h->N, (double*)h->stage[12]);
     stats_final_kernel<<<1, 32, 0, h->stream>>>((const double*)h->stage[12], nblk, dsum);
     CK(cudaGetLastError());

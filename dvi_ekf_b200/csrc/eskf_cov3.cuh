@@ -23,6 +23,9 @@
 #ifndef ESKF_OPT_FIN14
 #define ESKF_OPT_FIN14 0  // Joseph form: both sums of upd3_finish as one rolled loop of fourteen columns
 #endif
+#ifndef ESKF_OPT_ST2
+#define ESKF_OPT_ST2 0  // pass 2: the fetches of the head of the pass spread over its first multiply-adds
+#endif
 #ifndef ESKF_OPT_QP
 #define ESKF_OPT_QP 0  // process-noise diagonal as predicated adds
 #endif
@@ -201,6 +204,12 @@ ESKF_HD void fx3_apply_store_il(const double (&X)[24][3], const d2* f2, double* 
   for (int kb = 0; kb < 7; kb += 2) {
     Coefs<PS, 6> c;
     c.load(f2, FX3_H2 + 3 * kb);
+#if ESKF_OPT_ST1 == 2
+    if (kb == 0) {  // (two identity rows behind the first coefficient fetch: something to issue while it is in flight)
+      putX(9);
+      putX(10);
+    }
+#endif
 #pragma unroll
     for (int k = kb; k < kb + 2 && k < 7; ++k) {
       const int col = (k < 3) ? 9 + k : (k == 3) ? 15 : 19 + (k - 4);
@@ -208,7 +217,11 @@ ESKF_HD void fx3_apply_store_il(const double (&X)[24][3], const d2* f2, double* 
       for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int v = 0; v < 3; ++v) y[i][v] += c(3 * (k - kb) + i) * X[col][v];
+#if ESKF_OPT_ST1 == 2
+      if (k < 5) putX(k < 4 ? 11 + k : 17);
+#else
       putX(k < 6 ? 9 + k : 17);
+#endif
     }
   }
   // rows 18:21; between its nine columns: the finished rows 21:24, rows 0:3 (p += dt v) and the notch chain
@@ -330,6 +343,59 @@ ESKF_HD void fx3_apply_stream(double (&X)[24][3], const d2* f2, const double* ro
       for (int v = 0; v < 3; ++v) X[r0 + i][v] += c(o + i) * x[v];
   };
   double o0[3], o1[3], o2[3], o3[3], o4[3], o5[3], o16[3], o17[3], o18[3], o19[3], o22[3], o23[3];
+  Coefs<PS, 6> h2a, h2b;
+#if ESKF_OPT_ST2
+  // The pass starts with the row groups that need the fewest operands -- rows 3:9 on columns 6, 7 want three fetches of the
+  // tile -- and the other fetches of the head follow between the multiply-adds (as written before, six fetches of the tile,
+  // 18 LDS.128, stood in front of the first multiply-add, in every covariance warp of the CTA at once).  Every accumulator
+  // still sees the same operations in the same order.
+  {
+    double x6[3], x7[3];
+    ld(1, o2, o3);
+    ld(2, o4, o5);
+    ld(3, x6, x7);
+    Coefs<PS, 6> ab0, ab1, h1;
+    ab0.load(f2, FX3_AB);
+    ab1.load(f2, FX3_AB + 6);
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      X[3][v] = o3[v];
+      X[4][v] = o4[v];
+      X[5][v] = o5[v];
+      X[6][v] = 0.0;
+      X[7][v] = 0.0;
+      X[8][v] = 0.0;
+    }
+    ld(8, o16, o17);
+    ld(9, o18, o19);
+    col3(3, ab0, 0, x6);
+    col3(6, ab0, 3, x6);
+    h1.load(f2, FX3_H1);
+    ld(0, o0, o1);
+    col3(3, ab1, 0, x7);
+    col3(6, ab1, 3, x7);
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      X[18][v] = o16[v] + dt * o3[v];
+      X[19][v] = o17[v] + dt * o4[v];
+      X[20][v] = o18[v] + dt * o5[v];
+      X[16][v] = o16[v] + dt * o17[v];
+      X[17][v] = o17[v];
+    }
+    ld(11, o22, o23);
+    col3(18, h1, 0, x6);
+    col3(18, h1, 3, x7);
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      X[0][v] = o0[v] + dt * o3[v];
+      X[1][v] = o1[v] + dt * o4[v];
+      X[2][v] = o2[v] + dt * o5[v];
+      X[21][v] = 0.0;
+      X[22][v] = o22[v];
+      X[23][v] = o23[v];
+    }
+  }
+#else
   ld(1, o2, o3);
   ld(2, o4, o5);
   ld(8, o16, o17);
@@ -361,7 +427,6 @@ ESKF_HD void fx3_apply_stream(double (&X)[24][3], const d2* f2, const double* ro
     X[16][v] = o16[v] + dt * o17[v];
     X[17][v] = o17[v];
   }
-  Coefs<PS, 6> h2a, h2b;
   {  // columns 6, 7: C1 (rows 18:21), A and B (rows 3:9)
     double x6[3], x7[3];
     ld(3, x6, x7);
@@ -376,6 +441,7 @@ ESKF_HD void fx3_apply_stream(double (&X)[24][3], const d2* f2, const double* ro
     col3(3, ab, 0, x7);
     col3(6, ab, 3, x7);
   }
+#endif
   {  // columns 8, 9: C1 / C2, A and B; D on dof 1 (rows 21:24)
     double x8[3], x9[3];
     ld(4, x8, x9);

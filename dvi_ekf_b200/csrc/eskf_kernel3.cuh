@@ -103,6 +103,35 @@ struct PhaseTimer {  // (fire-and-forget global reductions: one register pair of
 #define PT_FLUSH()
 #endif
 
+// ESKF_EXP_JITTER (race-hunting build, tests/test_gpu_jitter.py): every synchronisation point of the role pipelines -- record
+// slot acquire / publish / wait / release, the barrier of the scalar roles, the JACOB -> CAMERA hand-over, the CTA barriers
+// around the camera update -- is preceded and followed by a pseudo-random, warp-uniform delay (hash of the jitter seed, CTA,
+// warp and a per-warp counter; 0 .. g_eskf_jitter_ns nanoseconds), which moves the roles against each other by whole steps.
+// A result that depends on the timing of the roles -- a missing ordering -- shows up as a difference against the plain build
+// (compute-sanitizer's racecheck is closed on this pool).  Not part of the product build.
+#if defined(ESKF_EXP_JITTER) && defined(ESKF_F)
+static __device__ unsigned int g_eskf_jitter_seed = 0, g_eskf_jitter_ns = 0;
+struct Jitter3 {
+  unsigned int n;
+  __device__ __forceinline__ void operator()() {
+    if (g_eskf_jitter_ns == 0) return;
+    unsigned int h = g_eskf_jitter_seed * 0x9E3779B9u ^ (blockIdx.x * 0x85EBCA6Bu) ^ ((threadIdx.x >> 5) * 0xC2B2AE35u) ^ (++n * 0x27D4EB2Fu);
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 12;
+    h *= 0x297A2D39u;
+    h ^= h >> 15;
+    if (h & 3u) return;  // three of four points pass undisturbed: delays come in bursts, not as a uniform slow-down
+    __nanosleep((h >> 2) % g_eskf_jitter_ns);
+  }
+};
+#define JIT() jit_()
+#define JIT_DECL() Jitter3 jit_{0}
+#else
+#define JIT()
+#define JIT_DECL()
+#endif
+
 // Filter.calculate_update_mse is evaluated by the STAGER role at this step of the NEXT epoch (see role3_stage)
 constexpr int STATS_IT3 = 2;
 
@@ -363,6 +392,7 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
   }
   __syncthreads();  // prologue
   PT_DECL();
+  JIT_DECL();
   int64_t k = 0;
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = epoch_steps3(a, c, e, k);
@@ -370,7 +400,9 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
       const int64_t kk = k + it;
 #if !ESKF_OPT_LATEACQ
       PT_MARK(1);
+      JIT();
       fx_slot_acquire(c.mbar, kk);  // the covariance warps are done with the record of step kk - 2
+      JIT();
       PT_MARK(0);
 #endif
 #if ESKF_OPT_LATEACQ
@@ -422,7 +454,9 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
       // The nominal step never reads the covariance: it is computed while the covariance warps still work on the record
       // that occupies this slot (step kk - 2); only the store of the rows waits for the slot.
       PT_MARK(1);
+      JIT();
       fx_slot_acquire(c.mbar, kk);
+      JIT();
       PT_MARK(0);
       if (act && ESKF3_SCALAR_ON(it)) {
         d2* dst = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
@@ -430,18 +464,28 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
         for (int j = FX3_AB / 2; j < FX3_MAIN / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
       }
 #endif
+      JIT();
       fx_slot_publish(c.mbar, kk);  // rows 3:9 of the record of step kk are in place
+      JIT();
       PT_MARK(1);
+      JIT();
       scalar_barrier();
+      JIT();
       PT_MARK(2);
     }
     k += n;
     if (!a.do_update) continue;
+    JIT();
     scalar_barrier();  // (an update-only launch has no step barrier: the measurement must be staged before U0)
+    JIT();
     PT_MARK(2);
     PT_MARK(5);
+    JIT();
     __syncthreads();  // U0 | U1
+    JIT();
+    JIT();
     __syncthreads();  // U1 | U2
+    JIT();
     PT_MARK(3);
     if (act) {
       if (sx[SX3_OK2 * F] != 0.0) {  // state (+) error state, IMU part (state.py:46-53,116-121)
@@ -482,7 +526,9 @@ __device__ __forceinline__ void role3_imu(const KArgs& a, const Ctx3& c, int lan
       }
     }
     PT_MARK(6);
+    JIT();
     scalar_barrier();  // U2 of the scalar roles done (the covariance warps do not wait: see role3_cov)
+    JIT();
     PT_MARK(2);
   }
   // ---- write back ----
@@ -533,6 +579,7 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
   }
   __syncthreads();  // prologue
   PT_DECL();
+  JIT_DECL();
   int64_t k = 0;
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = epoch_steps3(a, c, e, k);
@@ -540,7 +587,9 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
       const int64_t kk = k + it;
 #if !ESKF_OPT_LATEACQ
       PT_MARK(1);
+      JIT();
       fx_slot_acquire(c.mbar, kk);  // the covariance warps are done with the record of step kk - 2
+      JIT();
       PT_MARK(0);
 #endif
       if (act && ESKF3_SCALAR_ON(it)) {
@@ -567,7 +616,9 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
         if (EX && a.trace) trace_cam(a.trace + ((c.f0 + lane) * a.T + kk) * NX, pc, qc);
       }
       PT_MARK(1);
+      JIT();
       pk_ready_wait();
+      JIT();
       PT_MARK(4);  // JACOB has published the probe kinematics of the post-predict (dofs, notch): PK slot sn, TR
 #if ESKF_OPT_LATEACQ
       double fx[FX3_SIZE];  // (only the entries of rows 18:21 are ever touched: registers)
@@ -591,7 +642,9 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
         jac_rows_h1(a.model, dofs, pk, trv, Ro, dt, om_old, sig_om, fx);
       }
       PT_MARK(1);
+      JIT();
       fx_slot_acquire(c.mbar, kk);  // (see role3_imu: only the store waits for the slot)
+      JIT();
       PT_MARK(0);
       if (act && ESKF3_SCALAR_ON(it)) {
 #else
@@ -609,14 +662,20 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
         }
 #endif
       }
+      JIT();
       fx_slot_publish(c.mbar, kk);  // rows 18:21 of the record of step kk are in place
+      JIT();
       PT_MARK(1);
+      JIT();
       scalar_barrier();
+      JIT();
       PT_MARK(2);
     }
     k += n;
     if (!a.do_update) continue;
+    JIT();
     scalar_barrier();  // (an update-only launch has no step barrier: the measurement must be staged before U0)
+    JIT();
     PT_MARK(2);
     // ---- U0: residual (Filter.py:363-375) ----
     if (lane < F) {
@@ -642,8 +701,12 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
     }
     PT_MARK(5);
     PT_MARK(5);
+    JIT();
     __syncthreads();  // U0 | U1
+    JIT();
+    JIT();
     __syncthreads();  // U1 | U2
+    JIT();
     PT_MARK(3);
     PT_MARK(3);
     if (act) {
@@ -680,7 +743,9 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
       }
     }
     PT_MARK(6);
+    JIT();
     scalar_barrier();  // U2 of the scalar roles done (the covariance warps do not wait: see role3_cov)
+    JIT();
     PT_MARK(2);
   }
   if (act) {
@@ -735,6 +800,7 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
   }
   __syncthreads();  // prologue
   PT_DECL();
+  JIT_DECL();
   int64_t k = 0;
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = epoch_steps3(a, c, e, k);
@@ -742,7 +808,9 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
       const int64_t kk = k + it;
 #if !ESKF_OPT_LATEACQ
       PT_MARK(1);
+      JIT();
       fx_slot_acquire(c.mbar, kk);  // the covariance warps are done with the record of step kk - 2
+      JIT();
       PT_MARK(0);
 #endif
       if (act && ESKF3_SCALAR_ON(it)) {
@@ -760,7 +828,9 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
         put_notch(sn, notch, dofs);
         if (EX && a.trace) trace_dofs(a.trace + ((c.f0 + lane) * a.T + kk) * NX, dofs, notch);
       }
+      JIT();
       pk_ready_arrive();  // the CAMERA warp takes rows 18:21 from here
+      JIT();
 #if ESKF_OPT_LATEACQ
       double fx[FX3_SIZE];  // (rows 21:24 and, with IMU noise in Q, the noise rows: registers)
       if (act && ESKF3_SCALAR_ON(it)) {
@@ -780,7 +850,9 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
         }
       }
       PT_MARK(1);
+      JIT();
       fx_slot_acquire(c.mbar, kk);  // (see role3_imu: only the store waits for the slot)
+      JIT();
       PT_MARK(0);
       if (act && ESKF3_SCALAR_ON(it)) {
         d2* dst = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
@@ -830,18 +902,28 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
 #endif
       }
 #endif
+      JIT();
       fx_slot_publish(c.mbar, kk);  // dt, rows 21:24 (and the noise rows) of the record of step kk are in place
+      JIT();
       PT_MARK(1);
+      JIT();
       scalar_barrier();
+      JIT();
       PT_MARK(2);
     }
     k += n;
     if (!a.do_update) continue;
+    JIT();
     scalar_barrier();  // (an update-only launch has no step barrier: the measurement must be staged before U0)
+    JIT();
     PT_MARK(2);
     PT_MARK(5);
+    JIT();
     __syncthreads();  // U0 | U1
+    JIT();
+    JIT();
     __syncthreads();  // U1 | U2
+    JIT();
     PT_MARK(3);
     if (act) {
       if (sx[SX3_OK2 * F] != 0.0) {
@@ -856,7 +938,9 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
       }
     }
     PT_MARK(6);
+    JIT();
     scalar_barrier();  // U2 of the scalar roles done (the covariance warps do not wait: see role3_cov)
+    JIT();
     PT_MARK(2);
   }
   if (act) {
@@ -1060,6 +1144,7 @@ __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int l
   if (act && a.T > 0 && oap) stage_sample(0);
   __syncthreads();  // prologue
   PT_DECL();
+  JIT_DECL();
   int64_t k = 0;
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = epoch_steps3(a, c, e, k);
@@ -1072,12 +1157,16 @@ __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int l
       if (it >= n) break;
       if (act && k + it + 1 < a.T && ESKF3_SCALAR_ON(it)) stage_sample(k + it + 1);
       PT_MARK(1);
+      JIT();
       scalar_barrier();
+      JIT();
       PT_MARK(2);
     }
     k += n;
     if (!a.do_update) continue;
+    JIT();
     scalar_barrier();  // (an update-only launch has no step barrier: the measurement must be staged before U0)
+    JIT();
 #if ESKF_OPT_STATS_U0
     // error statistics of the PREVIOUS update, evaluated while the covariance warps form S, its inverse and the gain
     // (~9,000 cycles during which every scalar role waits): the parked copies are only overwritten after U1 | U2
@@ -1085,10 +1174,16 @@ __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int l
     (void)fl;
 #endif
     PT_MARK(5);
+    JIT();
     __syncthreads();  // U0 | U1
+    JIT();
+    JIT();
     __syncthreads();  // U1 | U2
+    JIT();
     PT_MARK(3);
+    JIT();
     scalar_barrier();  // U2 of the scalar roles done (the covariance warps do not wait: see role3_cov)
+    JIT();
 #if ESKF_OPT_PP
     pend = a.cam_ref && a.imu_ref && !a.snap;
 #else
@@ -1274,6 +1369,7 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
 #endif
   __syncthreads();  // prologue
   PT_DECL();
+  JIT_DECL();
 #ifdef ESKF_EXP_STAGGER  // (profiling experiment: the second covariance warp of every sub-partition starts late)
   if (ct >= 128) {
     const long long t0 = clock64();
@@ -1286,7 +1382,9 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = epoch_steps3(a, c, e, k);
     PT_MARK(15);
+    JIT();
     if (n > 0) fx_slot_wait(c.mbar, k);  // the Jacobian record of the first step of the epoch is complete
+    JIT();
     PT_MARK(0);
     const int n_ex = ESKF3_COV_ON ? n + (n & 1) : n;  // (one exchange more after an odd number of propagations)
     for (int it = 0; it < n_ex; ++it) {
@@ -1327,7 +1425,9 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
         fx3_apply_stream<F, RS3>(X, f2, TBR);
         PT_MARK(4);
         // the record of the NEXT step: its producers stored it one step ago (ESKF_OPT_LATEACQ) -- normally no wait
+        JIT();
         if (it + 1 < n) fx_slot_wait(c.mbar, kk + 1);
+        JIT();
         COV3_SYNCWARP();  // every lane of the filter is done with the buffer before pass 1 of the next step stores
         PT_MARK(3);
 #else
@@ -1335,7 +1435,9 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
         PT_MARK(2);
         // the record of the NEXT step is waited for here, behind the latency of the transposed reload, so that
         // nothing stands between the end of this step and the first coefficient fetch of the next one
+        JIT();
         if (it + 1 < n) fx_slot_wait(c.mbar, kk + 1);
+        JIT();
         COV3_SYNCWARP();
         PT_MARK(3);
         if (!step) break;
@@ -1350,7 +1452,9 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
         fx3_process_noise<F>(X, gl, f2, qdv, qd, imu_q);
 #endif
       }
+      JIT();
       fx_slot_release(c.mbar, kk);  // this warp is done with the record
+      JIT();
       PT_MARK(4);
     }
     k += n;
@@ -1369,7 +1473,9 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
     __syncwarp(gmask);
     const bool inv_ok = inv7_group3<4>(rec, cg, sxc + SX3_RD * F, F);
     PT_MARK(5);
+    JIT();
     __syncthreads();  // U0 | U1
+    JIT();
     PT_MARK(6);
     const bool upd_c = inv_ok && (sxc[SX3_OK * F] != 0.0);
     if (upd_c) {
@@ -1388,7 +1494,9 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
     }
     if (cg == 0) sxw[SX3_OK2 * F] = upd_c ? 1.0 : 0.0;
     PT_MARK(7);
+    JIT();
     __syncthreads();  // U1 | U2  (also orders the K / K R records of the eight lanes)
+    JIT();
     PT_MARK(8);
     if (upd_c) {
       upd3_w_pass<4>(X, cg, rec);

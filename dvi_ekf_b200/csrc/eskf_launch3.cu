@@ -54,3 +54,15 @@ extern "C" int eskf_debug_timing(long long* out) {
   return 0;
 }
 #endif
+
+#if defined(ESKF_EXP_JITTER)
+// race-hunting build only (eskf_kernel3.cuh, ESKF_EXP_JITTER): seed and largest delay [ns] of the injected jitter for this CTA
+// shape's translation unit; max_ns = 0 switches it off.  One entry point per shape: eskf_debug_set_jitter_<F>.
+#define ESKF_JIT_NAME2(f) eskf_debug_set_jitter_##f
+#define ESKF_JIT_NAME(f) ESKF_JIT_NAME2(f)
+extern "C" int ESKF_JIT_NAME(ESKF_F)(unsigned int seed, unsigned int max_ns) {
+  cudaError_t e = cudaMemcpyToSymbol(eskf::g_eskf_jitter_seed, &seed, sizeof(seed));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(eskf::g_eskf_jitter_ns, &max_ns, sizeof(max_ns));
+  return e == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -11,6 +11,7 @@
 //   rotated camera (with_notch) . dvi_ekf/models/Camera.py:172-208 (IMU source, initial state and error reference; the
 //                                 measurements stay those of the un-rotated camera, Filter.py:144-185)
 // One thread per camera frame for the derived data, one thread per interpolated instant for the IMU synthesis.
+#include <nvtx3/nvToolsExt.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -312,6 +313,8 @@ const char* eskf_prepass_last_error(void) { return g_pp_err.c_str(); }
 
 int eskf_prepass(int device, void* cuda_stream, const eskf_model_t* model, const eskf_prepass_in_t* in, const eskf_prepass_out_t* out,
                  int64_t* n_steps_out) {
+  nvtxRangePushA("eskf_prepass");
+  struct Pop { ~Pop() { nvtxRangePop(); } } nvtx_pop_;
   std::vector<void*> tmp;
   if (!model || !in || !out || !n_steps_out || in->n_frames < 2 || in->interframe_vals < 1 || !in->t || !in->xyz || !in->q_xyzw ||
       !out->x0 || !out->u0 || !out->dt || !out->om_acc || !out->n_prop || !out->cam || !out->notch || !out->cam_ref || !out->imu_ref) {

@@ -40,7 +40,16 @@ def allreduce_stats(stats_sum, group=None):
     import torch.distributed as dist
 
     if dist.is_available() and dist.is_initialized():
-        dist.all_reduce(stats_sum, op=dist.ReduceOp.SUM, group=group)
+        import torch
+
+        nvtx = stats_sum.is_cuda  # NVTX range on the timeline of a profiler
+        if nvtx:
+            torch.cuda.nvtx.range_push("eskf: all-reduce of the error statistics")
+        try:
+            dist.all_reduce(stats_sum, op=dist.ReduceOp.SUM, group=group)
+        finally:
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
     return stats_sum
 
 

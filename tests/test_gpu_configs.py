@@ -8,6 +8,9 @@ import pytest
 from tests.helpers import Scenario, cov_err, mandala_scenario, model_kwargs, state_err
 from oracle.eskf_oracle import OracleConfig
 
+# free-running bounds: ~3x the worst value measured on the B200 (printed with -s as "MEASURED ..."; profiles/r02_parity.md)
+TOL_SWEEP, TOL_STACK, TOL_RAGGED = 1e-8, 1e-8, 1e-8
+
 pytestmark = pytest.mark.gpu
 
 
@@ -51,7 +54,8 @@ def test_config3_tuning_sweep_per_filter_q_r_p0(golden, variant):
         xr, Pr, _, _ = kf.get_vectors()
         worst_s = max(worst_s, state_err(xg[i], xr))
         worst_P = max(worst_P, cov_err(Pg[i], Pr, Rd[i]))
-    assert worst_s < 1e-8 and worst_P < 1e-8, (worst_s, worst_P)  # free-running, 70 steps
+    print(f"MEASURED config3 sweep (70 free-running steps): state {worst_s:.2e} P {worst_P:.2e}")
+    assert worst_s < TOL_SWEEP and worst_P < TOL_SWEEP, (worst_s, worst_P)  # free-running, 70 steps
     assert np.abs(xg[0] - xg[35]).max() > 1e-9  # the tuning really changes the estimate
 
 
@@ -80,8 +84,9 @@ def test_config4_stacked_trajectories_33_samples_per_frame(golden, variant, fpt)
         kf = _run_oracle(s)
         xr, Pr, ur, Rr = kf.get_vectors()
         for i in (j * fpt, (j + 1) * fpt - 1):
-            assert state_err(xg[i], xr) < 1e-8, (names[j], state_err(xg[i], xr))  # free-running, 198 steps
-            assert cov_err(Pg[i], Pr, s.Rd) < 1e-8, (names[j], cov_err(Pg[i], Pr, s.Rd))
+            print(f"MEASURED config4 stacked {names[j]} (198 free-running steps): state {state_err(xg[i], xr):.2e} P {cov_err(Pg[i], Pr, s.Rd):.2e}")
+            assert state_err(xg[i], xr) < TOL_STACK, (names[j], state_err(xg[i], xr))  # free-running, 198 steps
+            assert cov_err(Pg[i], Pr, s.Rd) < TOL_STACK, (names[j], cov_err(Pg[i], Pr, s.Rd))
             assert np.abs(ug[i] - ur).max() < 1e-12
 
 
@@ -296,5 +301,6 @@ def test_ragged_and_empty_epochs(golden, variant):
     xr, Pr, ur, Rr = kf.get_vectors()
     assert np.all(status == 0) and np.allclose(st[:, 9], len(n_prop))
     for i in (0, 8):
-        assert state_err(xg[i], xr) < 1e-8 and cov_err(Pg[i], Pr, sc.Rd) < 1e-8
+        print(f"MEASURED ragged epochs (70 free-running steps): state {state_err(xg[i], xr):.2e} P {cov_err(Pg[i], Pr, sc.Rd):.2e}")
+        assert state_err(xg[i], xr) < TOL_RAGGED and cov_err(Pg[i], Pr, sc.Rd) < TOL_RAGGED
         assert np.abs(ug[i] - ur).max() < 1e-12 and np.abs(Rg[i] - Rr).max() < 1e-9

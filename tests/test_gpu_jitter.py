@@ -1,0 +1,43 @@
+"""Race evidence without compute-sanitizer (closed on this pool): the ESKF_EXP_JITTER build of the persistent kernel injects
+pseudo-random delays of up to a few microseconds -- about a whole IMU step -- before and after every synchronisation point of the
+role pipelines (record slot acquire / publish / wait / release, the barrier of the scalar roles, the JACOB -> CAMERA hand-over,
+the CTA barriers around the camera update), a different pattern per seed, CTA and warp.  Over 20 seeds, on the ragged-epoch
+case (epochs of 0, 1, 2, 17, 47 steps; ragged last CTA; three CTA shapes; in-kernel and pre-pass noise) and on the launch
+bench.py times, everything a launch leaves behind must be bit-identical to the plain build: an ordering that only holds by
+timing would show up as a different digest."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+JIT_LIB = os.path.join(ROOT, "dvi_ekf_b200", "libeskf_b200_jit.so")
+
+
+def _run(lib, seeds):
+    env = dict(os.environ)
+    if lib:
+        env["ESKF_B200_LIB"] = lib
+    else:
+        env.pop("ESKF_B200_LIB", None)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "jitter_run.py"), "--seeds", str(seeds)], env=env, cwd=ROOT,
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.strip().splitlines()
+    return lines[0], [l.split() for l in lines[1:]]
+
+
+def test_results_do_not_depend_on_the_timing_of_the_roles():
+    if not os.path.exists(JIT_LIB):
+        pytest.fail(f"{JIT_LIB} is missing: __graft_entry__.build() builds it (python tools/build_variants.py jit:ESKF_EXP_JITTER)")
+    head, plain = _run(None, 1)
+    assert "jitter_build=0" in head
+    want = {tuple(l[:-2]): l[-1] for l in plain}  # key: case and shape (without the seed), value: digest
+    head, jit = _run(JIT_LIB, 20)
+    assert "jitter_build=1" in head
+    assert len(jit) == 20 * len(plain)
+    bad = [l for l in jit if want[tuple(l[:-2])] != l[-1]]
+    assert not bad, bad[:5]

@@ -158,9 +158,10 @@ def test_legacy_preset_reproduces_reference_golden_file(BatchFilter, golden):
 
 
 def test_free_running_full_trajectory(BatchFilter, golden):
-    """140 frames x 10 IMU samples (1390 steps, 139 updates).  Two equally valid FP64 evaluation orders
-    of the REFERENCE algorithm already drift apart by ~4e-7 over this horizon, so the
-    free-running tolerance is horizon dependent: 2e-6 here."""
+    """140 frames x 10 IMU samples (1390 steps, 139 updates).  Free running, so the tolerance is horizon dependent: the
+    ORACLE answers a one-ulp perturbation of its inputs with 2e-8 (state) / 1e-9 (covariance) over this horizon
+    (DESIGN.md section 2).  Measured on the B200: 2.9e-8 / 1.5e-9 (eskf_kernel3), 2.1e-8 / 1.1e-9 (eskf_kernel); the bounds
+    are three times that, so a regression of the arithmetic shows."""
     sc = mandala_scenario(golden, n_frames=140, ifv=10)
     kf = sc.new_oracle()
     k = 0
@@ -175,8 +176,8 @@ def test_free_running_full_trajectory(BatchFilter, golden):
     err = max(state_err(xg[i], xr) for i in range(9))
     print(f"free-running 1390 steps: state {err:.2e}  P {cov_err(Pg[0], Pr, sc.Rd):.2e}")
     assert np.all(status == 0)
-    assert err < 2e-6
-    assert np.linalg.norm(Pg[0] - Pr) / np.linalg.norm(Pr) < 1e-8
+    assert err < 9e-8
+    assert cov_err(Pg[0], Pr, sc.Rd) < 5e-9 and np.linalg.norm(Pg[0] - Pr) / np.linalg.norm(Pr) < 5e-9
     # all replicas of a batch are bit-identical (no cross-filter coupling, no data races)
     assert all(np.array_equal(xg[0], xg[i]) and np.array_equal(Pg[0], Pg[i]) for i in range(9))
 
@@ -268,6 +269,7 @@ def test_free_running_low_process_noise(BatchFilter, golden, variant):
         xg, Pg, _, _, st = bf.get_state()
     assert np.all(st == 0)
     asym = np.abs(Pg[0] - Pg[0].T).max() / np.abs(Pg[0]).max()
+    print(f"MEASURED low process noise: state {state_err(xg[0], xr):.2e} P {cov_err(Pg[0], Pr, sc.Rd):.2e} asym {asym:.1e}")
     assert state_err(xg[0], xr) < 1e-7 and cov_err(Pg[0], Pr, sc.Rd) < 1e-7 and asym < 1e-11, (state_err(xg[0], xr), cov_err(Pg[0], Pr, sc.Rd), asym)
 
 
@@ -280,7 +282,7 @@ def test_free_running_unfrozen_dofs(BatchFilter, golden, variant):
     reference reports (Filter.calculate_dof_metric, printed with {:.2E}: Simulator.py:119,158) must agree in print."""
     from oracle.batch_oracle import BatchOracle
 
-    MAX_S = 1e-5  # worst of 256 filters (measured: see the printed distribution)
+    MAX_S = 3e-6  # worst of 256 filters (measured: see the printed distribution)
     sc = mandala_scenario(golden, n_frames=41, ifv=10, frozen_dofs=[False] * 6)
     rng = np.random.default_rng(5)
     n = 256
@@ -354,4 +356,5 @@ def test_free_running_ill_conditioned_tuning(BatchFilter, golden, variant, n_fra
         bf.run(sc.dt, sc.om_acc, sc.n_prop, sc.cam_meas, sc.notch_meas, want_stats=False)
         xg, Pg, _, _, st = bf.get_state()
     assert np.all(st == 0)
+    print(f"MEASURED ill-conditioned tuning ({n_frames} frames x {ifv}): state {state_err(xg[0], xr):.2e} P {cov_err(Pg[0], Pr, Rd):.2e}")
     assert state_err(xg[0], xr) < 1e-7 and cov_err(Pg[0], Pr, Rd) < 1e-7, (state_err(xg[0], xr), cov_err(Pg[0], Pr, Rd))
