@@ -235,6 +235,19 @@ def ncu_traffic():
     return None
 
 
+def _guard(launch, dev):
+    """One launch of a secondary workload: an exception on THIS rank (bad geometry, out of memory) must not leave the other
+    ranks waiting in the all-reduce that follows, so the launch is caught here and answered with a NaN vector; the
+    collective then still runs on every rank and the figure of the workload comes out as NaN."""
+    import torch
+
+    try:
+        return launch()
+    except Exception as e:
+        print(f"bench.py: secondary workload failed on this rank: {type(e).__name__}: {e}", file=sys.stderr, flush=True)
+        return torch.full((16,), float("nan"), dtype=torch.float64, device=dev)
+
+
 def _timed(fn, reset, reps, barrier, flush):
     """mean device time [ms] of `reps` calls of fn (CUDA events on torch's current stream, which is the handle's stream);
     one untimed warm-up call; `reset` (state reload) and the L2 flush sit outside the events"""
@@ -305,8 +318,8 @@ def secondary_workloads(a, wl, dev, local, rank, world, dist, flush, barrier):
         bf.set_noise(Qd, Rd, wl.sig_om[None])
 
         def run3():
-            st, sm = bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], cam_ref=d["cam_ref"], imu_ref=d["imu_ref"],
-                            stats_on_device=True, filter_id0=first)
+            sm = _guard(lambda: bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], cam_ref=d["cam_ref"],
+                                       imu_ref=d["imu_ref"], stats_on_device=True, filter_id0=first)[1], dev)
             allreduce_stats(sm)
             return sm
 
@@ -320,7 +333,10 @@ def secondary_workloads(a, wl, dev, local, rank, world, dist, flush, barrier):
 
     names = ["mandala0_mono", "mandala0_gt", "trans_x", "trans_y", "trans_z", "rot_x", "rot_y", "rot_z", "from_prop"]
     base, ifv4, frames, seeds_total = 50, 33, 200, 1024
-    seeds = seeds_total // world  # every rank: all nine trajectories x its share of the seeds
+    # every rank: all nine trajectories x its share of the seeds.  (The stacked-trajectory streams are indexed by the GLOBAL
+    # filter id -- trajectory = id / filters_per_traj -- so a rank keeps local ids 0 .. 9 * seeds and draws its own noise
+    # realisations from a rank-specific Philox key instead of an id offset.)
+    seeds = seeds_total // world
     idx = np.resize(np.concatenate((np.arange(base), np.arange(base - 2, 0, -1))), frames)  # there and back again
     tt = np.arange(frames) / 30.0
     ds = []
@@ -339,9 +355,9 @@ def secondary_workloads(a, wl, dev, local, rank, world, dist, flush, barrier):
         bf.set_noise(wl.Qd[None], wl.Rd[None], wl.sig_om[None])
 
         def run4():
-            st, sm = bf.run(w["dt"], w["oa"], w["npr"], w["cam"], w["notch"], cam_ref=w["cam_ref"], imu_ref=w["imu_ref"],
-                            n_traj=len(names), filters_per_traj=seeds, stats_on_device=True, seed=SEED,
-                            filter_id0=rank * n4, imu_noise_std=wl.imu_std, cam_noise_std=wl.cam_std)
+            sm = _guard(lambda: bf.run(w["dt"], w["oa"], w["npr"], w["cam"], w["notch"], cam_ref=w["cam_ref"],
+                                       imu_ref=w["imu_ref"], n_traj=len(names), filters_per_traj=seeds, stats_on_device=True,
+                                       seed=SEED + rank, imu_noise_std=wl.imu_std, cam_noise_std=wl.cam_std)[1], dev)
             allreduce_stats(sm)
             return sm
 
@@ -362,9 +378,9 @@ def secondary_workloads(a, wl, dev, local, rank, world, dist, flush, barrier):
         bf.set_noise(wl.Qd[None], wl.Rd[None], wl.sig_om[None])
 
         def run5():
-            st, sm = bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], cam_ref=d["cam_ref"], imu_ref=d["imu_ref"],
-                            stats_on_device=True, seed=SEED, filter_id0=first, imu_noise_std=wl.imu_std,
-                            cam_noise_std=wl.cam_std)
+            sm = _guard(lambda: bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], cam_ref=d["cam_ref"],
+                                       imu_ref=d["imu_ref"], stats_on_device=True, seed=SEED, filter_id0=first,
+                                       imu_noise_std=wl.imu_std, cam_noise_std=wl.cam_std)[1], dev)
             allreduce_stats(sm)
             return sm
 
@@ -383,9 +399,10 @@ def secondary_workloads(a, wl, dev, local, rank, world, dist, flush, barrier):
         bf.set_noise(wl.Qd[None], wl.Rd[None], wl.sig_om[None])
 
         def runc():
-            st, sm = bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], cam_ref=d["cam_ref"], imu_ref=d["imu_ref"],
-                            stats_on_device=True, seed=SEED, filter_id0=rank * nc, imu_noise_std=wl.imu_std,
-                            cam_noise_std=wl.cam_std, gt_dofs=tuple(wl.cfg.gt_imu_dofs))
+            sm = _guard(lambda: bf.run(d["dt"], d["oa"], d["npr"], d["cam"], d["notch"], cam_ref=d["cam_ref"],
+                                       imu_ref=d["imu_ref"], stats_on_device=True, seed=SEED, filter_id0=rank * nc,
+                                       imu_noise_std=wl.imu_std, cam_noise_std=wl.cam_std,
+                                       gt_dofs=tuple(wl.cfg.gt_imu_dofs))[1], dev)
             allreduce_stats(sm)
             return sm
 
@@ -428,7 +445,10 @@ def run_ours(a):
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=dev)
+        from datetime import timedelta
+
+        # (a rank that dies must take the job down within minutes, not after NCCL's default ten)
+        dist.init_process_group("nccl", device_id=dev, timeout=timedelta(seconds=240))
     n = a.filters
     first_id = rank * n
     imu_std, cam_std = wl.imu_std, wl.cam_std
@@ -558,7 +578,10 @@ def run_ours(a):
         sampler2 = ClockSampler(local)
         if rank == 0:
             sampler2.start()
-        secondary = secondary_workloads(a, wl, dev, local, rank, world, dist, flush, barrier)
+        try:
+            secondary = secondary_workloads(a, wl, dev, local, rank, world, dist, flush, barrier)
+        except Exception as e:  # the headline line must not depend on the secondary workloads
+            secondary = {"error": f"{type(e).__name__}: {e}"}
         clocks2 = sampler2.stop() if rank == 0 else None
 
     # max over ranks
@@ -611,8 +634,9 @@ def run_ours(a):
         }
         if secondary is not None:
             for v in secondary.values():
-                v["achieved_tflops"] = v["value"] * v["flops_per_filter_step"] * 1e-12
-                v["frac"] = v["achieved_tflops"] / peak_tf
+                if isinstance(v, dict):
+                    v["achieved_tflops"] = v["value"] * v["flops_per_filter_step"] * 1e-12
+                    v["frac"] = v["achieved_tflops"] / (peak_tf * world)  # of the FP64 peak of ALL GPUs of the job
             line["configs"] = secondary
             line["configs_clocks"] = clocks2
         print(json.dumps(line), flush=True)
