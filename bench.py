@@ -226,12 +226,13 @@ def measured_peaks():
 
 def ncu_traffic():
     """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p))
-        except Exception:
-            pass
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            try:
+                return json.load(open(p))
+            except Exception:
+                pass
     return None
 
 
@@ -598,7 +599,10 @@ def run_ours(a):
         peaks, which = measured_peaks()
         per_launch_flops = float(n) * T * F_MIN_PER_STEP
         ach = per_launch_flops / (ms * 1e-3) * 1e-12
-        alg_bytes = float(n) * (2 * (576 + 26 + 6 + 9) * 8 + 16 * 8) + (T * 7 + E * 21) * 8  # state in/out + streams
+        # state in / out + statistics row per filter, the shared streams, and the per-filter Monte-Carlo streams the pre-pass
+        # leaves in HBM for the persistent kernel (48 B per filter-step, 64 B per filter-update read, 112 B snapshot written)
+        alg_bytes = (float(n) * (2 * (576 + 26 + 6 + 9) * 8 + 16 * 8) + (T * 7 + E * 21) * 8
+                     + float(n) * (T * 48 + E * (64 + 112)))
         tr = ncu_traffic()
         roofline = {
             "bound": "fp64",

@@ -405,12 +405,14 @@ static const int kShapes3[] = {28, 16, 8, 4};              // eskf_kernel3
 
 static int kernel_of(const eskf_t* h) { return h->variant == 1 ? 1 : 3; }
 
-// Filters per CTA.  Must divide filters_per_traj when several trajectories are stacked (a CTA follows
-// ONE trajectory's epoch structure).  Every shape runs one CTA per SM (registers / shared memory) and a
-// wave of CTAs takes about the same time whatever its shape (per-step latency bound, profiles/r01_*): the
-// automatic choice minimises the number of waves and then prefers the larger shape.
+// Filters per CTA.  A CTA follows ONE trajectory's epoch structure: eskf_kernel3 cuts every trajectory's filters into
+// CTAs of their own (ragged last CTA per trajectory), the first kernel needs a shape that divides filters_per_traj.
+// Every shape runs one CTA per SM (registers / shared memory) and a wave of CTAs takes about the same time whatever
+// its shape (per-step latency bound, profiles/r01_*): the automatic choice minimises the number of waves and then
+// prefers the larger shape.
 static int pick_fpc(const eskf_t* h, int64_t fpt, bool multi_traj) {
-  auto fits = [&](int c) { return !multi_traj || (fpt % c) == 0; };
+  const bool k3 = kernel_of(h) == 3;
+  auto fits = [&](int c) { return !multi_traj || k3 || (fpt % c) == 0; };
   const int* shapes = kernel_of(h) == 3 ? kShapes3 : kShapes1;
   const int ns = kernel_of(h) == 3 ? 4 : 2;
   if (h->fpc > 0) {
@@ -422,7 +424,7 @@ static int pick_fpc(const eskf_t* h, int64_t fpt, bool multi_traj) {
   for (int i = 0; i < ns; ++i) {  // descending
     const int c = shapes[i];
     if (!fits(c)) continue;
-    const int64_t ctas = (h->N + c - 1) / c;
+    const int64_t ctas = (multi_traj && k3) ? ((h->N + fpt - 1) / fpt) * ((fpt + c - 1) / c) : (h->N + c - 1) / c;
     const int64_t waves = (ctas + h->sm_count - 1) / h->sm_count;
     if (best == 0 || waves < best_waves) {
       best = c;

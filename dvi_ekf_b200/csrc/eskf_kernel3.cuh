@@ -1521,16 +1521,31 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int F, int REG_S, int REG_C, bool EX>
+// MODE: bit 0 = export mode (FilterTraj rows, Jacobian record of the last step), bit 1 = stacked trajectories.  Separate
+// instantiations, so that the production kernel of a single-trajectory batch carries neither (a few integer instructions
+// in the prologue are enough to change the register allocation of the whole kernel).
+template <int F, int REG_S, int REG_C, int MODE>
 __global__ void __launch_bounds__(128 + 8 * F, 1) eskf_kernel3(const __grid_constant__ KArgs a) {
+  constexpr bool EX = (MODE & 1) != 0, MT = (MODE & 2) != 0;
   extern __shared__ __align__(16) double smem[];
   using L = Lay3<F>;
   constexpr int NTHR = 128 + 8 * F;
   const int tid = threadIdx.x;
   Ctx3 c;
   c.smem = smem;
-  c.f0 = (int64_t)blockIdx.x * F;
-  c.nf = (int)((a.N - c.f0) < F ? (a.N - c.f0) : F);
+  if constexpr (MT) {
+    // stacked trajectories: a CTA follows ONE trajectory's epoch structure, so every trajectory's filters_per_traj filters
+    // are cut into ceil(fpt / F) CTAs of their own (the last one ragged) -- fpt need not be a multiple of the CTA shape
+    const int64_t fpt = a.filters_per_traj, cpt = (fpt + F - 1) / F;
+    const int64_t tl = blockIdx.x / cpt, ch = blockIdx.x - tl * cpt;
+    c.f0 = tl * fpt + ch * F;
+    int64_t left = fpt - ch * F;
+    if (a.N - c.f0 < left) left = a.N - c.f0;
+    c.nf = (int)(left < F ? left : F);
+  } else {
+    c.f0 = (int64_t)blockIdx.x * F;
+    c.nf = (int)((a.N - c.f0) < F ? (a.N - c.f0) : F);
+  }
   c.gid0 = a.filter_id0 + c.f0;
   c.traj = (a.n_traj > 1) ? (c.gid0 / a.filters_per_traj) : 0;
   c.n_prop = a.n_prop ? a.n_prop + c.traj * a.E : nullptr;

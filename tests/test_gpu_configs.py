@@ -9,7 +9,7 @@ from tests.helpers import Scenario, cov_err, mandala_scenario, model_kwargs, sta
 from oracle.eskf_oracle import OracleConfig
 
 # free-running bounds: ~3x the worst value measured on the B200 (printed with -s as "MEASURED ..."; profiles/r02_parity.md)
-TOL_SWEEP, TOL_STACK, TOL_RAGGED = 1e-8, 1e-8, 1e-8
+TOL_SWEEP, TOL_STACK, TOL_RAGGED = 1e-10, 5e-11, 2e-11  # measured 3.4e-11, 1.3e-11, 3.7e-12
 
 pytestmark = pytest.mark.gpu
 
@@ -59,7 +59,9 @@ def test_config3_tuning_sweep_per_filter_q_r_p0(golden, variant):
     assert np.abs(xg[0] - xg[35]).max() > 1e-9  # the tuning really changes the estimate
 
 
-@pytest.mark.parametrize("variant,fpt", [(3, 8), (3, 28), (1, 12)])  # (v1 has the shapes 28 and 4: fpt 12 runs on 4)
+# (v1 has the shapes 28 and 4: fpt 12 runs on 4; eskf_kernel3 cuts every trajectory into CTAs of its own, ragged last one:
+# 13 and 37 filters per trajectory run on the 28-filter shape)
+@pytest.mark.parametrize("variant,fpt", [(3, 8), (3, 28), (1, 12), (3, 13), (3, 37)])
 def test_config4_stacked_trajectories_33_samples_per_frame(golden, variant, fpt):
     from dvi_ekf_b200 import BatchFilter
 
@@ -237,7 +239,7 @@ def test_tuner_objective_matches_oracle(golden, tmp_path):
             ref_upd[c, j] = acc / E
     rd, ru = ref_dof.mean(axis=1), ref_upd.mean(axis=1)
     print(f"tuner objective vs oracle: dof {np.abs(f_dof / rd - 1).max():.2e}, update {np.abs(f_upd / ru - 1).max():.2e}")
-    assert np.abs(f_dof / rd - 1).max() < 1e-8 and np.abs(f_upd / ru - 1).max() < 1e-8
+    assert np.abs(f_dof / rd - 1).max() < 1e-10 and np.abs(f_upd / ru - 1).max() < 1e-10  # measured 2.4e-11 / 6.6e-12
     assert abs(rd[0] / rd[1] - 1) > 1e-3 and ref_dof[0, 1] != ref_dof[0, 0]  # candidates and runs really differ
 
 

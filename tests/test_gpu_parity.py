@@ -270,7 +270,8 @@ def test_free_running_low_process_noise(BatchFilter, golden, variant):
     assert np.all(st == 0)
     asym = np.abs(Pg[0] - Pg[0].T).max() / np.abs(Pg[0]).max()
     print(f"MEASURED low process noise: state {state_err(xg[0], xr):.2e} P {cov_err(Pg[0], Pr, sc.Rd):.2e} asym {asym:.1e}")
-    assert state_err(xg[0], xr) < 1e-7 and cov_err(Pg[0], Pr, sc.Rd) < 1e-7 and asym < 1e-11, (state_err(xg[0], xr), cov_err(Pg[0], Pr, sc.Rd), asym)
+    # (measured 3.6e-10 / 5.8e-11 / 3.4e-13)
+    assert state_err(xg[0], xr) < 1.5e-9 and cov_err(Pg[0], Pr, sc.Rd) < 2e-10 and asym < 2e-12, (state_err(xg[0], xr), cov_err(Pg[0], Pr, sc.Rd), asym)
 
 
 @pytest.mark.parametrize("variant", [3, 1])
@@ -357,4 +358,5 @@ def test_free_running_ill_conditioned_tuning(BatchFilter, golden, variant, n_fra
         xg, Pg, _, _, st = bf.get_state()
     assert np.all(st == 0)
     print(f"MEASURED ill-conditioned tuning ({n_frames} frames x {ifv}): state {state_err(xg[0], xr):.2e} P {cov_err(Pg[0], Pr, Rd):.2e}")
-    assert state_err(xg[0], xr) < 1e-7 and cov_err(Pg[0], Pr, Rd) < 1e-7, (state_err(xg[0], xr), cov_err(Pg[0], Pr, Rd))
+    tol = 1e-7 if ifv == 33 else 1e-8  # measured 2.7e-8 / 8.2e-9 (12 frames x 33), 2.4e-9 / 1.4e-9 (31 frames x 10)
+    assert state_err(xg[0], xr) < tol and cov_err(Pg[0], Pr, Rd) < tol, (state_err(xg[0], xr), cov_err(Pg[0], Pr, Rd))
