@@ -270,6 +270,32 @@ def _timed(fn, reset, reps, barrier, flush):
     return float(np.mean(ms)), out
 
 
+CONFIG4_TRAJS = ["mandala0_mono", "mandala0_gt", "trans_x", "trans_y", "trans_z", "rot_x", "rot_y", "rot_z", "from_prop"]
+CONFIG4_SEEDS, CONFIG4_IFV, CONFIG4_FRAMES = 1024, 33, 200
+
+
+def secondary_plan(rank, world, filters_per_gpu):
+    """Who runs what in the secondary workloads: the launch geometry of every rank (filters, first GLOBAL filter id, stacked
+    trajectories), a pure function so that tests/test_multi_gpu.py can hold it against the argument checks of eskf_run for
+    every world size without a GPU (a plan that is valid on rank 0 only would leave the other ranks of a torchrun job
+    waiting in the all-reduce)."""
+    from dvi_ekf_b200.sharding import shard_of
+
+    f3, n3 = shard_of(16 ** 4, rank, world)
+    f5, n5 = shard_of(1 << 20, rank, world)
+    seeds = CONFIG4_SEEDS // world
+    return {
+        "config3": dict(n=n3, filter_id0=f3, n_traj=1, filters_per_traj=n3, total=16 ** 4),
+        # all nine trajectories x this rank's share of the seeds; LOCAL ids (the stacked streams are indexed by the global id:
+        # trajectory = id // filters_per_traj), independent noise per rank through the Philox key
+        "config4": dict(n=len(CONFIG4_TRAJS) * seeds, filter_id0=0, n_traj=len(CONFIG4_TRAJS), filters_per_traj=seeds,
+                        seed_offset=rank, total=len(CONFIG4_TRAJS) * seeds * world),
+        "config5": dict(n=n5, filter_id0=f5, n_traj=1, filters_per_traj=n5, total=1 << 20),
+        "calibration": dict(n=filters_per_gpu, filter_id0=rank * filters_per_gpu, n_traj=1, filters_per_traj=filters_per_gpu,
+                            total=filters_per_gpu * world),
+    }
+
+
 def secondary_workloads(a, wl, dev, local, rank, world, dist, flush, barrier):
     """BASELINE.json configs 3, 4, 5 and the calibration (all DOFs estimated) variant of config 2, timed in the same run
     as the headline, with the same clock sampler running.  Every rank works on its shard; the figures are max-over-ranks
@@ -301,9 +327,10 @@ def secondary_workloads(a, wl, dev, local, rank, world, dist, flush, barrier):
             out[name]["stats"] = stats
 
     # ---- config 3: 16^4 tuning grid, per-filter Q / R, noise-free streams (Simulator.py:163-245, config.yaml:76-82) ----
+    plan = secondary_plan(rank, world, a.filters)
     g = 16
     n3 = g ** 4
-    first, cnt = shard_of(n3, rank, world)
+    first, cnt = plan["config3"]["filter_id0"], plan["config3"]["n"]
     ga, gb, gc, gd = np.meshgrid(np.logspace(-2, 2, g), np.logspace(-2, 2, g), np.logspace(-3, 3, g), np.logspace(-3, 3, g),
                                  indexing="ij")
     sl = slice(first, first + cnt)
@@ -332,12 +359,12 @@ def secondary_workloads(a, wl, dev, local, rank, world, dist, flush, barrier):
     # ---- config 4: nine data/trajs trajectories x 1024 seeds, 33 IMU samples per frame, 200 frames, device pre-pass ----
     from dvi_ekf_b200.camera import load_trajectory
 
-    names = ["mandala0_mono", "mandala0_gt", "trans_x", "trans_y", "trans_z", "rot_x", "rot_y", "rot_z", "from_prop"]
-    base, ifv4, frames, seeds_total = 50, 33, 200, 1024
+    names = CONFIG4_TRAJS
+    base, ifv4, frames, seeds_total = 50, CONFIG4_IFV, CONFIG4_FRAMES, CONFIG4_SEEDS
     # every rank: all nine trajectories x its share of the seeds.  (The stacked-trajectory streams are indexed by the GLOBAL
     # filter id -- trajectory = id / filters_per_traj -- so a rank keeps local ids 0 .. 9 * seeds and draws its own noise
     # realisations from a rank-specific Philox key instead of an id offset.)
-    seeds = seeds_total // world
+    seeds = plan["config4"]["filters_per_traj"]
     idx = np.resize(np.concatenate((np.arange(base), np.arange(base - 2, 0, -1))), frames)  # there and back again
     tt = np.arange(frames) / 30.0
     ds = []
@@ -351,14 +378,15 @@ def secondary_workloads(a, wl, dev, local, rank, world, dist, flush, barrier):
              notch=cat(lambda x: x.notch), cam_ref=cat(lambda x: x.cam_ref), imu_ref=cat(lambda x: x.imu_ref),
              x0=torch.cat([x.x0[None].repeat(seeds, 1) for x in ds]).contiguous(),
              u0=torch.cat([x.u0[None].repeat(seeds, 1) for x in ds]).contiguous())
-    n4 = len(names) * seeds
+    n4 = plan["config4"]["n"]
     with BatchFilter(n4, device=local, **wl.model) as bf:
         bf.set_noise(wl.Qd[None], wl.Rd[None], wl.sig_om[None])
 
         def run4():
             sm = _guard(lambda: bf.run(w["dt"], w["oa"], w["npr"], w["cam"], w["notch"], cam_ref=w["cam_ref"],
                                        imu_ref=w["imu_ref"], n_traj=len(names), filters_per_traj=seeds, stats_on_device=True,
-                                       seed=SEED + rank, imu_noise_std=wl.imu_std, cam_noise_std=wl.cam_std)[1], dev)
+                                       seed=SEED + plan["config4"]["seed_offset"], filter_id0=plan["config4"]["filter_id0"],
+                                       imu_noise_std=wl.imu_std, cam_noise_std=wl.cam_std)[1], dev)
             allreduce_stats(sm)
             return sm
 
@@ -369,8 +397,8 @@ def secondary_workloads(a, wl, dev, local, rank, world, dist, flush, barrier):
     del w, ds
 
     # ---- config 5: 1,048,576 Monte-Carlo filters, sharded; NCCL all-reduce of the calibration statistics inside ----
-    n5 = 1 << 20
-    first, cnt = shard_of(n5, rank, world)
+    n5 = plan["config5"]["total"]
+    first, cnt = plan["config5"]["filter_id0"], plan["config5"]["n"]
     gen = torch.Generator(device=dev).manual_seed(7 + rank)
     x5 = t64(sc.x0).repeat(cnt, 1)
     x5[:, 10:13] += torch.randn((cnt, 3), generator=gen, dtype=torch.float64, device=dev) * np.deg2rad(3.0)

@@ -65,6 +65,32 @@ def _common_mem(args: Sequence[_Arg]) -> int:
     return mems.pop() if mems else MEM_HOST
 
 
+def check_run_geometry(n_filters: int, n_traj: int, filters_per_traj: int, filter_id0: int, n_steps: int, n_epochs: int,
+                       n_prop=None) -> None:
+    """The argument checks of ``eskf_run`` (csrc/eskf_api.cu), mirrored on the host so that a bad shard plan fails with a
+    clear ``ValueError`` before anything is launched: the kernels pick a filter's trajectory from its GLOBAL id,
+    ``(filter_id0 + f) // filters_per_traj``, and the sample stream by the running sum of ``n_prop``."""
+    if n_filters <= 0 or n_traj < 1 or n_steps < 0 or n_epochs < 0:
+        raise ValueError("n_filters, n_traj must be positive and n_steps, n_epochs non-negative")
+    if filter_id0 < 0:
+        raise ValueError("filter_id0 must be non-negative")
+    if n_traj > 1:
+        if filters_per_traj <= 0:
+            raise ValueError("filters_per_traj must be positive when several trajectories are stacked")
+        if filter_id0 % filters_per_traj:
+            raise ValueError("filter_id0 must be a multiple of filters_per_traj (a shard starts at a trajectory boundary)")
+        if filter_id0 + n_filters > n_traj * filters_per_traj:
+            raise ValueError(f"filter_id0 + n_filters = {filter_id0 + n_filters} exceeds n_traj * filters_per_traj = "
+                             f"{n_traj * filters_per_traj} (the streams of {n_traj} trajectories were passed)")
+    if isinstance(n_prop, np.ndarray):
+        npr = np.asarray(n_prop).reshape(n_traj, -1)
+        if (npr < 0).any():
+            raise ValueError("negative n_prop entry")
+        tot = npr.sum(axis=1)
+        if (tot > n_steps).any():
+            raise ValueError(f"sum(n_prop) = {int(tot.max())} exceeds n_steps = {n_steps}")
+
+
 class BatchFilter:
     """N independent VI-ESKF instances resident on one GPU."""
 
@@ -204,6 +230,8 @@ class BatchFilter:
         if aoa.rows != n_traj * T or acm.rows != n_traj * E or ano.rows != n_traj * E:
             raise ValueError("stream shapes do not match (n_traj, T, E)")
         mem = _common_mem([adt, anp, aoa, acm, ano, acr, air])
+        check_run_geometry(self.n, n_traj, int(filters_per_traj if filters_per_traj else self.n), int(filter_id0), T, E,
+                           n_prop if isinstance(n_prop, np.ndarray) else None)
         s = EskfStreams()
         s.n_steps, s.n_epochs, s.n_traj, s.mem = T, E, n_traj, mem
         s.filters_per_traj = int(filters_per_traj if filters_per_traj else self.n)

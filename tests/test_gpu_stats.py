@@ -130,7 +130,7 @@ def test_prepass_path_is_bit_identical_to_the_in_kernel_path(golden, fpc):
     assert np.isfinite(out[0][0]).all() and out[0][5][:, 8].min() > 0
 
 
-def test_run_rejects_inconsistent_stream_geometry(golden):
+def test_run_rejects_inconsistent_stream_geometry(golden, monkeypatch):
     """eskf_run's argument checks (the kernels index trajectories by the GLOBAL filter id and the sample stream by the running
     sum of n_prop): a shard that does not start at a trajectory boundary, filters beyond the last trajectory and epochs
     that add up to more steps than the stream holds are refused with ESKF_EINVAL instead of reading out of bounds."""
@@ -143,13 +143,21 @@ def test_run_rejects_inconsistent_stream_geometry(golden):
         bf.set_noise(sc.Qd[None], sc.Rd[None], sc.sig_om[None])
         bf.set_state(s.x0[None], sc.P0[None], s.u0[None], None)
         args = (two(s.dt), two(s.om_acc), two(s.n_prop), two(s.cam), two(s.notch))
-        with pytest.raises(EskfError, match="exceeds n_traj"):
+        with pytest.raises((EskfError, ValueError), match="exceeds n_traj"):
             bf.run(*args, n_traj=2, filters_per_traj=10)  # 40 filters, streams for 20
-        with pytest.raises(EskfError, match="multiple of filters_per_traj"):
+        with pytest.raises((EskfError, ValueError), match="multiple of filters_per_traj"):
             bf.run(*args, n_traj=2, filters_per_traj=32, filter_id0=8)
         bad = s.n_prop.copy()
         bad[3] += 5
-        with pytest.raises(EskfError, match="exceeds n_steps"):
+        with pytest.raises((EskfError, ValueError), match="exceeds n_steps"):
             bf.run(s.dt, s.om_acc, bad, s.cam, s.notch)
+        import dvi_ekf_b200.engine as eng
+
+        with monkeypatch.context() as m:  # past the host-side mirror of the checks: the C ABI refuses on its own
+            m.setattr(eng, "check_run_geometry", lambda *a, **k: None)
+            with pytest.raises(EskfError, match="exceeds n_traj"):
+                bf.run(*args, n_traj=2, filters_per_traj=10)
+            with pytest.raises(EskfError, match="exceeds n_steps"):
+                bf.run(s.dt, s.om_acc, bad, s.cam, s.notch)
         st, sm = bf.run(*args, n_traj=2, filters_per_traj=20)  # the consistent call still runs
         assert sm[11] == 40

@@ -91,3 +91,39 @@ def test_world_size_2_gloo_reproduces_the_single_process_statistics():
     out = summarise_stats(res[0][3])
     assert out["filters"] == n_total and len(out["dof_rmse"]) == 6
     assert np.isclose(out["dof_metric_mean"], ref[6] / n_total)
+
+
+def test_bench_secondary_plan_is_valid_on_every_rank():
+    """bench.py's `configs` block (BASELINE configs 3 / 4 / 5 + calibration) at 1 / 2 / 4 / 8 GPUs: the launch geometry of EVERY
+    rank passes the argument checks of eskf_run (mirrored by engine.check_run_geometry) and the shards add up to the whole job.
+    (A plan valid on rank 0 only leaves the other ranks of a torchrun job waiting in the all-reduce: round 2 lost ten minutes
+    of a 2-GPU box to exactly that.)"""
+    import bench
+    from dvi_ekf_b200.engine import check_run_geometry
+
+    for world in (1, 2, 4, 8):
+        plans = [bench.secondary_plan(r, world, 4096) for r in range(world)]
+        for name in ("config3", "config4", "config5", "calibration"):
+            assert sum(p[name]["n"] for p in plans) == plans[0][name]["total"]
+            for p in plans:
+                g = p[name]
+                check_run_geometry(g["n"], g["n_traj"], g["filters_per_traj"], g["filter_id0"], 1390, 139)
+        for name in ("config3", "config5", "calibration"):  # contiguous global ids
+            ids = [(p[name]["filter_id0"], p[name]["n"]) for p in plans]
+            assert ids[0][0] == 0 and all(a[0] + a[1] == b[0] for a, b in zip(ids, ids[1:]))
+        assert len({p["config4"]["seed_offset"] for p in plans}) == world  # independent noise per rank
+
+
+def test_run_geometry_checks():
+    from dvi_ekf_b200.engine import check_run_geometry
+
+    check_run_geometry(40, 2, 20, 0, 110, 11, np.full(22, 10, dtype=np.int32))
+    check_run_geometry(20, 2, 20, 20, 110, 11)  # the second trajectory's shard
+    with pytest.raises(ValueError, match="exceeds n_traj"):
+        check_run_geometry(40, 2, 10, 0, 110, 11)
+    with pytest.raises(ValueError, match="exceeds n_traj"):
+        check_run_geometry(4608, 9, 512, 4608, 6567, 199)  # the round-2 bug: a global id offset on local streams
+    with pytest.raises(ValueError, match="multiple of filters_per_traj"):
+        check_run_geometry(40, 2, 32, 8, 110, 11)
+    with pytest.raises(ValueError, match="exceeds n_steps"):
+        check_run_geometry(4, 1, 4, 0, 110, 11, np.array([10] * 10 + [15], dtype=np.int32))
