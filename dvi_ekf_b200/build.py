@@ -83,7 +83,7 @@ def build_cuda(force: bool = False, verbose: bool = False, defines=(), suffix: s
             sys.stdout.write(o)
     objs = [o for (o, _, _) in jobs]
     if force or todo or not _newer(LIB, objs):
-        _run([_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"], os.path.join(OBJ, "link.log"))
+        _run([_nvcc(), "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"], os.path.join(OBJ, "link.log"))
     return LIB
 
 

@@ -523,7 +523,8 @@ ESKF_HD void fx3_noise_diag(int g, const QD& qd, double (&qdv)[3]) {
 }
 
 // Fi Q Fi^T for the tile of lane group g (Filter.py:349).
-template <int PS, typename QD>
+// IQ = false compiles the IMU-noise part out (a caller that knows Q[0:6] = 0 for its filters).
+template <int PS, bool IQ = true, typename QD>
 ESKF_HD void fx3_process_noise(double (&X)[24][3], int g, const d2* f2, const double (&qdv)[3], const QD& qd, bool imu_q) {
   // diagonal entries P'(3g+v, 3g+v) = X[3g+v][v]: every index is a constant
 #if ESKF_OPT_QP
@@ -543,7 +544,7 @@ ESKF_HD void fx3_process_noise(double (&X)[24][3], int g, const d2* f2, const do
     for (int v = 0; v < 3; ++v) X[3 * j + v][v] += (g == j) ? qdv[v] : 0.0;
   X[17][2] += (g == 5) ? qdv[2] : 0.0;
 #endif
-  if (imu_q && (g == 2 || g == 6 || g == 7)) {
+  if (IQ && imu_q && (g == 2 || g == 6 || g == 7)) {
     // n_om drives theta (I), p_C (Np) and theta_C (Nt): L Q_om L^T on rows/cols {6:9,18:21,21:24};
     // the diagonal of the theta block was added above.
     auto at = [&](int j) {

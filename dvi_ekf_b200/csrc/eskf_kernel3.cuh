@@ -34,6 +34,7 @@
 // Register budget by role (setmaxnreg): scalar warps shrink to REG_S, covariance warps grow to REG_C
 // (eskf_launch3.cu).
 #pragma once
+#include <type_traits>
 #include "eskf_cov3.cuh"
 #include "eskf_kernel.cuh"
 
@@ -67,6 +68,9 @@
 #endif
 #ifndef ESKF_OPT_TMA
 #define ESKF_OPT_TMA 0  // sample stream staged by cp.async.bulk chunks (see CH3_STEPS)
+#endif
+#ifndef ESKF_OPT_COLD
+#define ESKF_OPT_COLD 0  // covariance role: re-orientation and IMU-noise code outside the step loop
 #endif
 #ifndef ESKF_OPT_ADDR
 #define ESKF_OPT_ADDR 0  // covariance role: buffer offsets kept in (laundered) registers instead of being re-derived every step
@@ -1329,6 +1333,9 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
   const d2* fxb = reinterpret_cast<const d2*>(c.smem + L::FXB) + cf;
   auto qd = [&](int j) { return sxc[(SX3_QD + j) * F]; };
   const bool imu_q = (qd(3) != 0.0) || (qd(4) != 0.0) || (qd(5) != 0.0);
+#if ESKF_OPT_COLD
+  const bool warp_iq = __any_sync(0xffffffffu, imu_q);  // (warp-uniform: which copy of the step loop this warp runs)
+#endif
   double qdv[3];  // diagonal process noise of this lane's three rows
   fx3_noise_diag(cg, qd, qdv);
 
@@ -1386,6 +1393,54 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
     if (n > 0) fx_slot_wait(c.mbar, k);  // the Jacobian record of the first step of the epoch is complete
     JIT();
     PT_MARK(0);
+#if ESKF_OPT_COLD
+    // The step loop holds nothing but the two passes: the re-orientation after an odd number of propagations follows the loop,
+    // and the IMU-noise part of Fi Q Fi^T (Q[0:6] != 0: never with config.yaml, where the filter is built with dt = 0) lives in a
+    // second copy of the loop that a warp enters only if one of its four filters needs it.  As written before, both sat
+    // inside the loop body (82 + 320 instructions between and behind the passes) and were fetched with it on every step: the
+    // role loops of this kernel exceed the instruction cache, their code comes from L2 again and again.
+    auto step_loop = [&](auto IQ) {
+      constexpr bool iq = decltype(IQ)::value;
+      for (int it = 0; it < n; ++it) {
+        const int64_t kk = k + it;
+        if (ESKF3_COV_ON) {
+          const d2* f2 = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
+          fx3_apply_store_il<F, RS3>(X, f2, Tb + 3 * cg);
+          COV3_SYNCWARP();
+          PT_MARK(1);
+          fx3_apply_stream<F, RS3>(X, f2, Tb + 3 * cg * RS3);
+          PT_MARK(4);
+          JIT();
+          if (it + 1 < n) fx_slot_wait(c.mbar, kk + 1);
+          JIT();
+          COV3_SYNCWARP();  // every lane of the filter is done with the buffer before pass 1 of the next step stores
+          PT_MARK(3);
+          int gl = cg;
+          asm volatile("" : "+r"(gl));
+#ifndef ESKF_EXP_NO_QNOISE
+          fx3_process_noise<F, iq>(X, gl, f2, qdv, qd, imu_q);
+#endif
+        }
+        JIT();
+        fx_slot_release(c.mbar, kk);  // this warp is done with the record
+        JIT();
+        PT_MARK(4);
+      }
+    };
+    if (warp_iq)
+      step_loop(std::true_type{});
+    else
+      step_loop(std::false_type{});
+    if (ESKF3_COV_ON && (n & 1)) {  // (one exchange more after an odd number of propagations: the tile is turned back)
+#pragma unroll
+      for (int i = 0; i < 24; ++i)
+#pragma unroll
+        for (int v = 0; v < 3; ++v) Tb[i * RS3 + 3 * cg + v] = X[i][v];
+      COV3_SYNCWARP();
+      load_rows();
+      COV3_SYNCWARP();
+    }
+#else
     const int n_ex = ESKF3_COV_ON ? n + (n & 1) : n;  // (one exchange more after an odd number of propagations)
     for (int it = 0; it < n_ex; ++it) {
       const int64_t kk = k + it;
@@ -1449,7 +1504,7 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
         int gl = cg;
         asm volatile("" : "+r"(gl));
 #ifndef ESKF_EXP_NO_QNOISE
-        fx3_process_noise<F>(X, gl, f2, qdv, qd, imu_q);
+        fx3_process_noise<F, true>(X, gl, f2, qdv, qd, imu_q);
 #endif
       }
       JIT();
@@ -1457,6 +1512,7 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
       JIT();
       PT_MARK(4);
     }
+#endif
     k += n;
     if (!a.do_update) continue;
     // ---- U0: S and its inverse (the scalar CAMERA role computes the residual meanwhile) ----
