@@ -69,6 +69,9 @@
 #ifndef ESKF_OPT_TMA
 #define ESKF_OPT_TMA 0  // sample stream staged by cp.async.bulk chunks (see CH3_STEPS)
 #endif
+#ifndef ESKF_OPT_H1S
+#define ESKF_OPT_H1S 0  // rows 18:21 of Fx formed by the STAGER role when it is idle (pre-pass noise / noise-free runs)
+#endif
 #ifndef ESKF_OPT_COLD
 #define ESKF_OPT_COLD 0  // covariance role: re-orientation and IMU-noise code outside the step loop
 #endif
@@ -366,6 +369,20 @@ __device__ __forceinline__ void trace_dofs(double* r, const double* dofs, const 
   for (int i = 0; i < 3; ++i) r[16 + i] = notch[i];
 }
 
+// Which scalar role forms rows 18:21 of Fx (Filter._cam_error_jacobian: C1, C2).  The CAMERA warp shares its sub-partition
+// with two covariance warps and was the busiest scalar role there (~680 instructions per step against the 2 x ~700 of the
+// covariance warps), while the STAGER warp of ITS sub-partition has next to nothing to do once the Monte-Carlo generator runs
+// in the pre-pass (or the run is noise free): then it takes this block.  With the generator inside the kernel (batches whose
+// pre-pass buffers do not fit) and in export mode the CAMERA warp keeps it.  Same function, same inputs: bit-identical.
+template <bool EX>
+__device__ __forceinline__ bool h1_by_stager(const KArgs& a) {
+#if ESKF_OPT_H1S
+  return !EX && (a.imu_pf != nullptr || !a.noise_on);
+#else
+  return false;
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // role 0: IMU nominal state
 template <int F, int NTHR, bool EX>
@@ -584,6 +601,7 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
   __syncthreads();  // prologue
   PT_DECL();
   JIT_DECL();
+  const bool h1s = h1_by_stager<EX>(a);  // rows 18:21 of Fx are the STAGER's work in this launch (see role3_stage)
   int64_t k = 0;
   for (int64_t e = 0; e < a.E; ++e) {
     const int n = epoch_steps3(a, c, e, k);
@@ -592,7 +610,7 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
 #if !ESKF_OPT_LATEACQ
       PT_MARK(1);
       JIT();
-      fx_slot_acquire(c.mbar, kk);  // the covariance warps are done with the record of step kk - 2
+      if (!h1s) fx_slot_acquire(c.mbar, kk);  // the covariance warps are done with the record of step kk - 2
       JIT();
       PT_MARK(0);
 #endif
@@ -621,13 +639,13 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
       }
       PT_MARK(1);
       JIT();
-      pk_ready_wait();
+      if (!h1s) pk_ready_wait();
       JIT();
       PT_MARK(4);  // JACOB has published the probe kinematics of the post-predict (dofs, notch): PK slot sn, TR
 #if ESKF_OPT_LATEACQ
       double fx[FX3_SIZE];  // (only the entries of rows 18:21 are ever touched: registers)
 #endif
-      if (act && ESKF3_SCALAR_ON(it)) {
+      if (!h1s && act && ESKF3_SCALAR_ON(it)) {
         // rows 18:21 of Fx (Filter._cam_error_jacobian, Filter.py:270-342): the half of the Jacobian work that
         // only needs the probe kinematics, R_WB_old and om_old -- taken off JACOB, the longest scalar role
         const double* uo = sx + (SX3_RING + 8 * (int)(kk & 3)) * F;
@@ -667,7 +685,7 @@ __device__ __forceinline__ void role3_cam(const KArgs& a, const Ctx3& c, int lan
 #endif
       }
       JIT();
-      fx_slot_publish(c.mbar, kk);  // rows 18:21 of the record of step kk are in place
+      if (!h1s) fx_slot_publish(c.mbar, kk);  // rows 18:21 of the record of step kk are in place
       JIT();
       PT_MARK(1);
       JIT();
@@ -965,11 +983,40 @@ __device__ __forceinline__ void role3_jac(const KArgs& a, const Ctx3& c, int lan
 
 // ---------------------------------------------------------------------------------------------
 // role 3: sample-stream stager + Monte-Carlo noise
-template <int F, int NTHR>
+template <int F, int NTHR, bool EX>
 __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int lane) {
   using L = Lay3<F>;
   const bool act = lane < c.nf;
   double* sx = c.smem + L::SX + lane;
+  const bool h1s = h1_by_stager<EX>(a);
+  d2* fxb = reinterpret_cast<d2*>(c.smem + L::FXB) + lane;  // pair j2 of slot s at fxb[(s * FX3_NPAIR + j2) * F]
+  const TRView<F> trv{sx + SX3_TR * F};
+  double sig_om[3] = {0, 0, 0};
+  if (h1s && act) {
+    const double* pg = a.par + (c.f0 + lane) * PAR_STRIDE;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) sig_om[i] = pg[PAR_SIGOM + i];
+  }
+  // rows 18:21 of the Jacobian record of step kk (what role3_cam does otherwise)
+  auto rows_h1 = [&](int64_t kk) {
+    const double* uo = sx + (SX3_RING + 8 * (int)(kk & 3)) * F;
+    const double dt = sx[(SX3_RING + 8 * (int)((kk + 1) & 3) + 6) * F];
+    const int s = (int)(kk & 1), sn = s ^ 1;
+    const PKView<F> pk{sx + (SX3_PK + PK3 * sn) * F};
+    double om_old[3], Ro[9], dofs[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      om_old[i] = uo[i * F];
+      dofs[3 + i] = sx[(SX3_PK + PK3 * sn + 17 + i) * F];
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Ro[i] = sx[(SX3_RO + 9 * s + i) * F];
+    double fx[FX3_SIZE];
+    jac_rows_h1(a.model, dofs, pk, trv, Ro, dt, om_old, sig_om, fx);
+    d2* dst = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
+#pragma unroll
+    for (int j = FX3_H1 / 2; j < FX3_AB / 2; ++j) dst[j * F] = d2{fx[2 * j], fx[2 * j + 1]};
+  };
   const int64_t gid = a.noise_mod > 0 ? (c.gid0 + lane) % a.noise_mod : c.gid0 + lane;  // id the noise is keyed by
 #if ESKF_OPT_PP
   // pre-pass mode: the (noisy) samples of every filter were prepared by eskf_pp_streams_kernel -- same generator, same sums
@@ -1160,6 +1207,17 @@ __device__ __forceinline__ void role3_stage(const KArgs& a, const Ctx3& c, int l
 #endif
       if (it >= n) break;
       if (act && k + it + 1 < a.T && ESKF3_SCALAR_ON(it)) stage_sample(k + it + 1);
+      if (h1s) {
+        JIT();
+        fx_slot_acquire(c.mbar, k + it);  // the covariance warps are done with the record of step kk - 2
+        JIT();
+        pk_ready_wait();  // JACOB has published the probe kinematics of the post-predict
+        JIT();
+        if (act && ESKF3_SCALAR_ON(it)) rows_h1(k + it);
+        JIT();
+        fx_slot_publish(c.mbar, k + it);  // rows 18:21 of the record of step kk are in place
+        JIT();
+      }
       PT_MARK(1);
       JIT();
       scalar_barrier();
@@ -1647,7 +1705,7 @@ __global__ void __launch_bounds__(128 + 8 * F, 1) eskf_kernel3(const __grid_cons
     else if (warp == 1)
       role3_cam<F, NTHR, EX>(a, c, lane);
     else if (warp == 2)
-      role3_stage<F, NTHR>(a, c, lane);
+      role3_stage<F, NTHR, EX>(a, c, lane);
     else
       role3_jac<F, NTHR, EX>(a, c, lane);
   }

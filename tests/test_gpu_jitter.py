@@ -31,8 +31,15 @@ def _run(lib, seeds):
 
 
 def test_results_do_not_depend_on_the_timing_of_the_roles():
-    if not os.path.exists(JIT_LIB):
-        pytest.fail(f"{JIT_LIB} is missing: __graft_entry__.build() builds it (python tools/build_variants.py jit:ESKF_EXP_JITTER)")
+    if not os.path.exists(JIT_LIB):  # normally built by __graft_entry__.build(); a fresh checkout builds it here (nvcc, ~30 s)
+        from dvi_ekf_b200 import build as b
+
+        obj, lib = b.OBJ, b.LIB
+        try:
+            b.build_cuda(defines=("ESKF_EXP_JITTER",), suffix="_jit")
+        finally:
+            b.OBJ, b.LIB = obj, lib
+    assert os.path.exists(JIT_LIB)
     head, plain = _run(None, 1)
     assert "jitter_build=0" in head
     want = {tuple(l[:-2]): l[-1] for l in plain}  # key: case and shape (without the seed), value: digest
