@@ -1459,7 +1459,7 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
     // role loops of this kernel exceed the instruction cache, their code comes from L2 again and again.
     auto step_loop = [&](auto IQ) {
       constexpr bool iq = decltype(IQ)::value;
-      for (int it = 0; it < n; ++it) {
+      auto one_step = [&](int it) {
         const int64_t kk = k + it;
         if (ESKF3_COV_ON) {
           const d2* f2 = fxb + ((int)(kk & 1) * FX3_NPAIR) * F;
@@ -1483,7 +1483,19 @@ __device__ __forceinline__ void role3_cov(const KArgs& a, const Ctx3& c, int ct)
         fx_slot_release(c.mbar, kk);  // this warp is done with the record
         JIT();
         PT_MARK(4);
+      };
+#if ESKF_OPT_COLD == 2
+      // two steps per trip: the instruction fetch restarts at every taken branch (~115 cycles at the loop head and at the
+      // reconvergence before it, and the first ~25 lines of pass 1 arrive late), once per two steps instead of once per step
+      int it = 0;
+      for (; it + 1 < n; it += 2) {
+        one_step(it);
+        one_step(it + 1);
       }
+      if (it < n) one_step(it);
+#else
+      for (int it = 0; it < n; ++it) one_step(it);
+#endif
     };
     if (warp_iq)
       step_loop(std::true_type{});
